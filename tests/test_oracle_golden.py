@@ -1,0 +1,65 @@
+"""Pins the oracle (oracle/*.py) to the reference: golden fixtures made by
+executing /root/reference (tests/golden/make_golden.py)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import TINY, load_golden
+from oracle import dpm_oracle, uvit_oracle
+
+
+def test_interp_docstring_kat():
+    # dpm_solver_pp.py:21-24
+    xp, yp = torch.tensor([0.0, 1.0]), torch.tensor([0.0, 2.0])
+    assert float(dpm_oracle._pwl(torch.tensor(0.5), xp, yp)) == 1.0
+    assert float(dpm_oracle._pwl(torch.tensor(-10.0), xp, yp)) == -20.0
+
+
+def test_schedule_bit_exact():
+    g, _ = load_golden("schedule.npz")
+    s = dpm_oracle.Schedule()
+    for i, t in enumerate(g["t"]):
+        assert float(s.log_mean(t)) == float(g["log_alpha"][i])
+        assert float(s.sigma(t)) == float(g["sigma"][i])
+        assert float(s.lam(t)) == float(g["lam"][i])
+        assert float(s.inv_lam(g["lam"][i])) == float(g["inv_lam"][i])
+
+
+@pytest.mark.parametrize("name,separate", [("single", False), ("two", True)])
+def test_forward_matches_reference(name, separate):
+    g, sd = load_golden(f"tiny_{name}.npz")
+    cfg = dict(TINY, separate=separate)
+    noise, y = uvit_oracle.uvit_forward(sd, cfg, g["x"], g["t"], g["ctx"], g["m"])
+    assert torch.allclose(noise, g["noise"], rtol=0, atol=2e-6)
+    assert torch.allclose(y, g["y"], rtol=0, atol=2e-6)
+    n2 = uvit_oracle.uvit_forward(sd, cfg, g["x"], g["t"], g["ctx"], None)
+    assert torch.allclose(n2, g["noise_nomask"], rtol=0, atol=2e-6)
+
+
+@pytest.mark.parametrize("name,separate", [("single", False), ("two", True)])
+@pytest.mark.parametrize("steps", [20, 7, 9])
+def test_joint_sample_matches_reference(name, separate, steps):
+    g, sd = load_golden(f"tiny_{name}.npz")
+    cfg = dict(TINY, separate=separate)
+    z, pm = dpm_oracle.joint_sample(sd, cfg, g["x"], g["m"], g["ctx"], g["empty"], float(g["scale"]), steps)
+    ref_z, ref_pm = g[f"z{steps}"], g[f"pm{steps}"]
+    assert (z - ref_z).abs().max() <= 2e-4 * ref_z.abs().max()
+    assert (pm - ref_pm).abs().max() <= 2e-4
+
+
+def test_multistep_bit_exact():
+    g, _ = load_golden("multistep.npz")
+    s = dpm_oracle.Solver(None, dpm_oracle.Schedule())
+    t = [g["t"][i] for i in range(4)]
+    m2 = s.multistep_second(g["x"], [g["X1"], g["X0"]], [t[1], t[2]], t[3])
+    m3 = s.multistep_third(g["x"], [g["X2"], g["X1"], g["X0"]], [t[0], t[1], t[2]], t[3])
+    assert torch.equal(m2, g["m2"])
+    assert torch.equal(m3, g["m3"])
+
+
+def test_bits_roundtrip():
+    ids = torch.arange(256).reshape(1, 1, 16, 16)
+    bits = dpm_oracle.int2bits(ids)
+    assert bits.shape == (1, 8, 16, 16)
+    assert int(bits[0, 0, 15, 15]) == 1 and int(bits[0, 7, 0, 1]) == 1  # MSB first
+    assert torch.equal(dpm_oracle.bits2int((bits * 2.0 - 1.0) > 0).long(), ids)
