@@ -1,0 +1,154 @@
+/*
+ * pdm.h -- C ABI of libpdm.so: the B200 (sm_100a) joint image+mask sampling hot path of
+ * Panoptic Diffusion Models (U-ViT t2i forward wrapped in the DPM-Solver++ data-prediction loop).
+ *
+ * The reference is pure Python (no FFI of its own); each entry point below names the reference
+ * function it replaces (paths relative to the reference tree).  INTEGRATION.md shows the ctypes
+ * binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error; pdm_last_error() gives the message
+ *     (thread-local).
+ *   - all tensor pointers are DEVICE pointers to contiguous float32 unless stated otherwise and are
+ *     owned by the caller; the engine owns its parameters and a private workspace.
+ *   - all device work is enqueued on the cudaStream_t passed as `stream` (void*; NULL = legacy
+ *     default stream); no function synchronises the stream except where noted.
+ *   - a handle is thread-compatible (one thread at a time), one handle per GPU/process.
+ *   - there is NO CPU path: every entry point that computes needs a CUDA device.
+ */
+#ifndef PDM_H_
+#define PDM_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PDM_ABI_VERSION 1
+
+/* precision modes of the network evaluation */
+#define PDM_PREC_BF16 0 /* bf16 operands on tcgen05 tensor cores, fp32 accumulate, fp32 residual stream */
+#define PDM_PREC_FP32 1 /* fp32 everywhere (parity anchor: <=1e-3 max-rel vs the reference forward) */
+
+/* number of floats per model evaluation in a solver plan (see pdm_sample) */
+#define PDM_PLAN_STRIDE 16
+/* plan record layout (float32 each):
+ *  [0] t_model   time fed to the network (= 1000 * t_continuous, train_t2i_discrete.py:508)
+ *  [1] alpha     alpha(t_eval)   [2] sigma   sigma(t_eval)      (dpm_solver_pp.py:313-316)
+ *  [3] A         sigma(t_next)/sigma(s)                coefficient of the step-start state
+ *  [4] B_img     signed coefficient of X_0 (image)     [5] C_img  signed coefficient of (X_j - X_0)
+ *  [6] B_msk     signed coefficient of P_0 (mask)      [7] C_msk  signed coefficient of (P_j - P_0)
+ *  [8] stage     0,1,2 : index of this evaluation inside its solver step
+ *  [9] has_c     1 if the (X_j - X_0) term is present (stage > 0)
+ *  [10] last     1 if this evaluation closes its solver step (output becomes the next step-start state)
+ *  [11..15] reserved (0)
+ */
+
+typedef struct pdm_engine* pdm_handle;
+
+/* Mirrors the keyword arguments of libs/uvit_t2i.py:259-261 (UViT.__init__) that shape the graph. */
+typedef struct pdm_config {
+    int32_t img_size;           /* latent H = W (32 @256px, 64 @512px) */
+    int32_t patch_size;         /* 2 */
+    int32_t in_chans;           /* 4 */
+    int32_t embed_dim;          /* D, multiple of 64 */
+    int32_t depth;              /* even */
+    int32_t num_heads;          /* D / 64 (head dim must be 64) */
+    int32_t mlp_ratio;          /* 4 */
+    int32_t clip_dim;           /* 768 */
+    int32_t num_clip_token;     /* 77 */
+    int32_t num_panoptic_class; /* 8 analog bits */
+    int32_t enable_panoptic;    /* 1: mask_embed / decoder_pred_mask exist */
+    int32_t separate;           /* 1: two-stream topology (mask blocks + zero-conv bridges) */
+} pdm_config;
+
+/* replaces: utils.py:291-299 get_nnet / UViT.__init__ (libs/uvit_t2i.py:259-353) */
+int pdm_create(const pdm_config* cfg, pdm_handle* out);
+int pdm_destroy(pdm_handle h);
+
+/* replaces: nn.Module.load_state_dict (eval_t2i_discrete.py:51).  `key` is the reference state_dict
+ * key, `dev_f32` a device float32 tensor of the given shape; the engine copies and
+ * repacks it (fp32 master + bf16 GEMM operand).  Unknown key -> error.  Dead-but-present keys
+ * (mask_embed_0.*, even-indexed zero_convs.*) are accepted and ignored. */
+int pdm_set_param(pdm_handle h, const char* key, const void* dev_f32, const int64_t* shape, int32_t ndim,
+                  void* stream);
+/* checks that every parameter the graph needs was set; builds bf16 operands.  Synchronises `stream`. */
+int pdm_finalize_params(pdm_handle h, void* stream);
+
+/* bytes of private workspace the engine will hold for `n` network rows (n = samples in one forward) */
+int pdm_workspace_bytes(pdm_handle h, int32_t n, int32_t precision, size_t* bytes);
+
+/* replaces: UViT.forward (libs/uvit_t2i.py:378-525).
+ *   x [n,in_chans,H,W]; t [n] (model time, e.g. 0..1000); ctx [n,num_clip_token,clip_dim];
+ *   mask [n,num_panoptic_class,H,W] or NULL (image-only path, uvit_t2i.py:407-410);
+ *   out_noise [n,in_chans,H,W]; out_mask [n,num_panoptic_class,H,W] (required iff mask != NULL). */
+int pdm_nnet_forward(pdm_handle h, const float* x, const float* t, const float* ctx, const float* mask,
+                     float* out_noise, float* out_mask, int32_t n, int32_t precision, void* stream);
+
+/* replaces: cfg_nnet's guidance combine (train_t2i_discrete.py:429-431) + DPM_Solver.model_fn's
+ * eps->x0 (dpm_solver_pp.py:316) + one singlestep linear update (dpm_solver_pp.py:444-456, 529-555,
+ * 724-764), fused in ONE elementwise kernel.  `coef` is a HOST pointer to one plan record.
+ *   eps_c/eps_u [B,4hw] (eps_u NULL -> no guidance), pm_c/pm_u [B,8hw] (NULL -> no mask stream),
+ *   x_in  state the network was evaluated at; x_base step-start state (== x_in at stage 0);
+ *   X0/P0 data-prediction history of stage 0 (written at stage 0, read later);
+ *   x_out/m_out next state.  m_in is not needed (the mask "x0" is the prediction itself). */
+int pdm_cfg_update(const float* eps_c, const float* eps_u, const float* pm_c, const float* pm_u,
+                   const float* x_in, const float* x_base, float* X0, float* x_out,
+                   const float* m_base, float* P0, float* m_out,
+                   const float* coef, float cfg_scale, int64_t n_img, int64_t n_mask, void* stream);
+
+/* replaces: DPM_Solver.sample(method='fast') (dpm_solver_pp.py:1018-1044) driven by cfg_nnet
+ * (train_t2i_discrete.py:387-439, 506-516): the whole denoising loop on the device.
+ *   plan: HOST array [n_evals][PDM_PLAN_STRIDE] built by the host planner (solver scalars are data
+ *   independent); z_init [B,4,H,W]; mask_init [B,8,H,W] (NULL = image-only);
+ *   ctx [B,T,clip]; empty_ctx [T,clip] (NULL -> no guidance, cfg_scale ignored);
+ *   out_z [B,4,H,W]; out_pred_mask [B,8,H,W] = CFG'd mask prediction of the first evaluation of the
+ *   last solver step (dpm_solver_pp.py:827,1044).
+ * use_graph != 0 captures the loop into a CUDA graph (cached per (B, n_evals, precision)). */
+int pdm_sample(pdm_handle h, const float* plan, int32_t n_evals, const float* z_init, const float* mask_init,
+               const float* ctx, const float* empty_ctx, float cfg_scale, float* out_z, float* out_pred_mask,
+               int32_t B, int32_t precision, int32_t use_graph, void* stream);
+
+/* replaces: utils.py:490-518 bits2int applied to (pred_mask > 0) (utils.py:596): sign-threshold the 8
+ * analog bits, MSB first.  pred_mask [B,8,H,W] float32 -> labels [B,H,W] int32 (device). */
+int pdm_bits2int(const float* pred_mask, int32_t* labels, int32_t B, int32_t nbits, int32_t hw, void* stream);
+/* replaces: utils.py:475-488 int2bits followed by *2-1 (train_t2i_discrete.py:489-490):
+ * ids [B,H,W] int32 -> analog bits [B,8,H,W] float32 in {-1,+1}. */
+int pdm_int2bits(const int32_t* ids, float* bits, int32_t B, int32_t nbits, int32_t hw, void* stream);
+
+/* diagnostics */
+const char* pdm_last_error(void);
+int pdm_abi_version(void);
+/* number of kernels launched by this library since load (all handles); lets a caller count launches
+ * inside a timed region. */
+int64_t pdm_launch_count(void);
+/* per-forward timing hooks: when enabled the engine records CUDA events around named phases. */
+int pdm_set_profiling(pdm_handle h, int32_t enabled);
+/* after a forward with profiling enabled (synchronises): milliseconds spent in up to `cap` phases;
+ * names are written as a '\n'-separated list into name_buf. */
+int pdm_get_profile(pdm_handle h, float* ms, int32_t cap, char* name_buf, int32_t name_cap, int32_t* count);
+
+/* ---- kernel-level diagnostics (unit tests, per-kernel roofline timing in bench.py) ---------------
+ * One Linear layer through the production GEMM kernel of the given precision:
+ *   out[M,N] = [gelu](A[M,K] . W[N,K]^T + bias) [+ resid]   (all float32 device tensors; for
+ *   PDM_PREC_BF16 A and W are rounded to bf16 first, exactly as the engine feeds the tcgen05 kernel).
+ * If A2/K2 are given the K loop streams [A | A2] (the long-skip GEMM).  iters > 0 and ms != NULL:
+ * the GEMM kernel alone is launched `iters` extra times between CUDA events and the average duration
+ * (milliseconds) is written to *ms (synchronises). */
+int pdm_debug_linear(const float* A, const float* A2, const float* W, const float* bias, const float* resid,
+                     float* out, int32_t M, int32_t N, int32_t K, int32_t K2, int32_t precision, int32_t gelu,
+                     int32_t iters, float* ms, void* stream);
+/* Self-attention core through the production kernel: qkv [nb,L,3*H*64] -> out [nb,L,H*64] (float32
+ * device tensors, rounded to bf16 for PDM_PREC_BF16); same timing convention. */
+int pdm_debug_attention(const float* qkv, float* out, int32_t nb, int32_t L, int32_t H, int32_t precision,
+                        int32_t iters, float* ms, void* stream);
+/* LayerNorm kernel: x [rows,D] -> out (float32 result; bf16 path rounds through bf16); timing as above. */
+int pdm_debug_layernorm(const float* x, const float* w, const float* b, float* out, int64_t rows, int32_t D,
+                        int32_t precision, int32_t iters, float* ms, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PDM_H_ */

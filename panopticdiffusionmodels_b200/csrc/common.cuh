@@ -1,0 +1,156 @@
+// Shared host/device helpers for libpdm.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <stdexcept>
+#include <string>
+
+namespace pdm {
+
+typedef __nv_bfloat16 bf16;
+
+struct Error : public std::runtime_error {
+    explicit Error(const std::string& s) : std::runtime_error(s) {}
+};
+
+#define PDM_CHECK_CUDA(expr)                                                                              \
+    do {                                                                                                  \
+        cudaError_t _e = (expr);                                                                          \
+        if (_e != cudaSuccess)                                                                            \
+            throw ::pdm::Error(std::string(#expr) + " failed: " + cudaGetErrorString(_e) + " (" __FILE__ ":" + \
+                               std::to_string(__LINE__) + ")");                                           \
+    } while (0)
+
+#define PDM_REQUIRE(cond, msg)                                                  \
+    do {                                                                        \
+        if (!(cond)) throw ::pdm::Error(std::string("pdm: ") + (msg));          \
+    } while (0)
+
+extern std::atomic<long long> g_launch_count;
+inline void count_launch() { g_launch_count.fetch_add(1, std::memory_order_relaxed); }
+inline void check_launch(const char* what) {
+    count_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) throw Error(std::string(what) + " launch failed: " + cudaGetErrorString(e));
+}
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
+
+// Row addressing of a logically [nb * Lr, width] matrix living inside a [nb, bs, width] buffer:
+// logical row m = b * Lr + t  ->  physical row b * bs + t.
+struct RowMap {
+    int Lr;  // logical rows per batch
+    int bs;  // physical rows per batch (>= Lr)
+};
+
+// ---- GEMM interface shared by the SIMT fp32 kernel and the tcgen05 bf16 kernel ----
+// out = [gelu]( A1[:, :K1] . W[:, :K1]^T + A2[:, :K2] . W[:, K1:]^T + bias ) [+ resid]
+//   A*: activation dtype (fp32 in PDM_PREC_FP32, bf16 in PDM_PREC_BF16), row-major, width K*
+//   W : [N, K1+K2] row-major (nn.Linear layout), fp32 master + bf16 copy
+//   out32 (fp32, may alias resid) and/or out2 (activation dtype)
+struct GemmProblem {
+    const void* A1 = nullptr;
+    const void* A2 = nullptr;
+    int K1 = 0, K2 = 0;
+    int a1_bs = 0, a2_bs = 0;  // physical rows per batch of A1 / A2
+    const float* W32 = nullptr;
+    const bf16* W16 = nullptr;
+    const float* bias = nullptr;
+    int N = 0;
+    int nb = 1, Lr = 0;  // logical rows = nb * Lr
+    const float* resid = nullptr;
+    int resid_bs = 0;
+    float* out32 = nullptr;
+    int out32_bs = 0;
+    void* out2 = nullptr;
+    int out2_bs = 0;
+    bool gelu = false;
+};
+
+void gemm_simt_f32(const GemmProblem& p, cudaStream_t s);
+void gemm_tc_bf16(const GemmProblem& p, cudaStream_t s);
+
+// ---- attention: qkv [nb, L, 3D] (q | k | v, each H heads x 64) -> out [nb, L, D] ----
+void attention_simt(const void* qkv, void* out, int nb, int L, int H, bool is_bf16, cudaStream_t s);
+void attention_tc_bf16(const bf16* qkv, bf16* out, int nb, int L, int H, cudaStream_t s);
+
+// ---- bandwidth-bound kernels (elementwise.cu) ----
+void layernorm(const float* x, const float* w, const float* b, void* out, bool out_bf16, long long rows, int D,
+               cudaStream_t s);
+void convert_f32_bf16(const float* in, bf16* out, long long n, cudaStream_t s);
+void copy_rows(void* dst, int dst_bs, const void* src, int src_bs, int Lr, int nb, int row_bytes, cudaStream_t s);
+
+struct EmbedArgs {
+    const float* img;      // [Bx, C, S, S]
+    const float* mask;     // [Bx, Cm, S, S] or null
+    int Bx;                // input batch (rows b use input b % Bx)
+    int nb;                // output batch
+    const float* t_dev;    // [Bx] or null
+    float t_scalar;
+    const float* freqs;    // [D/2]
+    const float* ctxtok;   // [nb, T, D] (bias already added)
+    const float* w_img;    // [D, C*p*p]
+    const float* b_img;
+    const float* w_msk;    // [D, Cm*p*p]
+    const float* b_msk;
+    const float* pos;      // [ext + P (+P), D]
+    const float* pos_m;    // positional table of the mask tokens, indexed by patch
+    float* out_x;          // [nb, Lx, D]
+    int Lx;
+    float* out_m;          // [nb, Lm, D] mask tokens written at token offset m_off
+    int Lm, m_off;
+    int C, Cm, S, p, D, T;
+};
+void embed_tokens(const EmbedArgs& a, cudaStream_t s);
+
+struct HeadArgs {
+    const float* x;       // [nb, Lx, D] image tokens at offset x_off
+    int Lx, x_off;
+    const float* m;       // [nb, Lm, D] mask tokens at offset m_off (null: image only)
+    int Lm, m_off;
+    bool ln_m;            // apply the final LayerNorm to the mask tokens too (single-stream)
+    const float* ln_w;
+    const float* ln_b;
+    const float* w_dec;   // [p*p*C, D]
+    const float* b_dec;
+    const float* w_decm;  // [p*p*Cm, D]
+    const float* b_decm;
+    const float* w_fin;   // [C, C, 3, 3]
+    const float* b_fin;
+    const float* w_finm;  // [Cm, Cm, 3, 3]
+    const float* b_finm;
+    float* tmp_img;       // [nb, C, S, S]
+    float* tmp_msk;       // [nb, Cm, S, S]
+    float* out_img;       // [nb, C, S, S]
+    float* out_msk;       // [nb, Cm, S, S]
+    int nb, C, Cm, S, p, D;
+};
+void head_decode(const HeadArgs& a, cudaStream_t s);
+
+struct UpdateArgs {
+    const float* eps_c;
+    const float* eps_u;
+    const float* pm_c;
+    const float* pm_u;
+    const float* x_in;
+    const float* x_base;
+    float* X0;
+    float* x_out;
+    const float* m_base;
+    float* P0;
+    float* m_out;
+    float alpha, sigma, A, B_img, C_img, B_msk, C_msk, scale;
+    int stage, has_c;
+    long long n_img, n_mask;
+};
+void cfg_solver_update(const UpdateArgs& a, cudaStream_t s);
+
+void bits2int(const float* pm, int32_t* labels, int B, int nbits, int hw, cudaStream_t s);
+void int2bits(const int32_t* ids, float* bits, int B, int nbits, int hw, cudaStream_t s);
+
+}  // namespace pdm

@@ -1,0 +1,431 @@
+// HBM-bound kernels of the hot path: LayerNorm, token embed, head decode, concat copies,
+// the fused CFG + DPM-Solver++ update (K12) and the analog-bit codec.
+// All are plain vectorised SIMT kernels; their roofline is HBM bandwidth.
+#include "common.cuh"
+
+namespace pdm {
+
+std::atomic<long long> g_launch_count{0};
+
+// ----------------------------------------------------------------------------------------------
+// LayerNorm (libs/uvit_t2i.py:142,166,328 -> nn.LayerNorm(D), eps 1e-5, affine), one warp per row.
+// Algorithmic bytes: rows * D * (4 read + 2|4 write).
+// ----------------------------------------------------------------------------------------------
+template <int NV, typename OutT>
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                        const float* __restrict__ b, OutT* __restrict__ out,
+                                                        long long rows, int D) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const float4* xr = reinterpret_cast<const float4*>(x + row * D);
+    float4 v[NV];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = lane + 32 * i;  // float4 index
+        if (c * 4 < D) {
+            v[i] = __ldg(xr + c);
+            sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        } else {
+            v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / (float)D;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = lane + 32 * i;
+        if (c * 4 < D) {
+            const float a = v[i].x - mean, bb = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
+            sq += (a * a + bb * bb) + (cc * cc + d * d);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = rsqrtf(sq / (float)D + 1e-5f);
+    const float4* w4 = reinterpret_cast<const float4*>(w);
+    const float4* b4 = reinterpret_cast<const float4*>(b);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = lane + 32 * i;
+        if (c * 4 < D) {
+            const float4 ww = __ldg(w4 + c), bb = __ldg(b4 + c);
+            float4 y;
+            y.x = (v[i].x - mean) * rstd * ww.x + bb.x;
+            y.y = (v[i].y - mean) * rstd * ww.y + bb.y;
+            y.z = (v[i].z - mean) * rstd * ww.z + bb.z;
+            y.w = (v[i].w - mean) * rstd * ww.w + bb.w;
+            if constexpr (sizeof(OutT) == 4) {
+                reinterpret_cast<float4*>(out + row * D)[c] = y;
+            } else {
+                __nv_bfloat162 lo = __floats2bfloat162_rn(y.x, y.y), hi = __floats2bfloat162_rn(y.z, y.w);
+                uint2 pk;
+                pk.x = *reinterpret_cast<uint32_t*>(&lo);
+                pk.y = *reinterpret_cast<uint32_t*>(&hi);
+                reinterpret_cast<uint2*>(out + row * D)[c] = pk;
+            }
+        }
+    }
+}
+
+template <int NV>
+static void launch_ln(const float* x, const float* w, const float* b, void* out, bool out_bf16, long long rows, int D,
+                      cudaStream_t s) {
+    const int wpb = 8;
+    const unsigned grid = (unsigned)ceil_div_ll(rows, wpb);
+    if (out_bf16)
+        layernorm_kernel<NV, bf16><<<grid, wpb * 32, 0, s>>>(x, w, b, (bf16*)out, rows, D);
+    else
+        layernorm_kernel<NV, float><<<grid, wpb * 32, 0, s>>>(x, w, b, (float*)out, rows, D);
+    check_launch("layernorm");
+}
+
+void layernorm(const float* x, const float* w, const float* b, void* out, bool out_bf16, long long rows, int D,
+               cudaStream_t s) {
+    PDM_REQUIRE(D % 4 == 0 && D <= 2048, "layernorm: D must be a multiple of 4 and <= 2048");
+    const int nv = ceil_div(D, 128);
+    if (nv <= 1) launch_ln<1>(x, w, b, out, out_bf16, rows, D, s);
+    else if (nv <= 2) launch_ln<2>(x, w, b, out, out_bf16, rows, D, s);
+    else if (nv <= 4) launch_ln<4>(x, w, b, out, out_bf16, rows, D, s);
+    else if (nv <= 6) launch_ln<6>(x, w, b, out, out_bf16, rows, D, s);
+    else if (nv <= 8) launch_ln<8>(x, w, b, out, out_bf16, rows, D, s);
+    else launch_ln<16>(x, w, b, out, out_bf16, rows, D, s);
+}
+
+// ----------------------------------------------------------------------------------------------
+__global__ void convert_kernel(const float4* __restrict__ in, uint2* __restrict__ out, long long n4) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n4; i += stride) {
+        const float4 v = __ldg(in + i);
+        __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&lo);
+        pk.y = *reinterpret_cast<uint32_t*>(&hi);
+        out[i] = pk;
+    }
+}
+void convert_f32_bf16(const float* in, bf16* out, long long n, cudaStream_t s) {
+    PDM_REQUIRE(n % 4 == 0, "convert: n must be a multiple of 4");
+    const long long n4 = n / 4;
+    const int grid = (int)std::min<long long>(ceil_div_ll(n4, 256), 148 * 16);
+    convert_kernel<<<grid, 256, 0, s>>>((const float4*)in, (uint2*)out, n4);
+    check_launch("convert");
+}
+
+// copy [nb, Lr, row_bytes] between buffers with different batch strides (two-stream concat)
+__global__ void copy_rows_kernel(uint4* __restrict__ dst, long long dst_bs16, const uint4* __restrict__ src,
+                                 long long src_bs16, long long per_batch16, int nb) {
+    const long long total = per_batch16 * nb;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < total; i += stride) {
+        const long long b = i / per_batch16, r = i - b * per_batch16;
+        dst[b * dst_bs16 + r] = __ldg(src + b * src_bs16 + r);
+    }
+}
+void copy_rows(void* dst, int dst_bs, const void* src, int src_bs, int Lr, int nb, int row_bytes, cudaStream_t s) {
+    PDM_REQUIRE(row_bytes % 16 == 0, "copy_rows: row_bytes must be a multiple of 16");
+    const long long r16 = row_bytes / 16;
+    const long long per = (long long)Lr * r16;
+    const int grid = (int)std::min<long long>(ceil_div_ll(per * nb, 256), 148 * 16);
+    copy_rows_kernel<<<grid, 256, 0, s>>>((uint4*)dst, (long long)dst_bs * r16, (const uint4*)src,
+                                          (long long)src_bs * r16, per, nb);
+    check_launch("copy_rows");
+}
+
+// ----------------------------------------------------------------------------------------------
+// Token embed (libs/uvit_t2i.py:382-406): time token | context tokens | image patches | mask patches,
+// + positional embedding, written straight into the residual stream(s).  One block per (token, row).
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) embed_kernel(EmbedArgs a) {
+    const int tok = blockIdx.x;  // 0 .. ext + P + (mask ? P : 0)
+    const int b = blockIdx.y;
+    const int ext = 1 + a.T;
+    const int g = a.S / a.p;
+    const int P = g * g;
+    const int bi = b % a.Bx;
+    __shared__ float patch[64];
+    if (tok == 0) {
+        const float t = a.t_dev ? a.t_dev[bi] : a.t_scalar;
+        const int half = a.D / 2;
+        float* o = a.out_x + ((long long)b * a.Lx) * a.D;
+        for (int d = threadIdx.x; d < a.D; d += blockDim.x) {
+            float v = 0.f;
+            if (d < 2 * half) {
+                const float arg = t * a.freqs[d < half ? d : d - half];
+                v = d < half ? cosf(arg) : sinf(arg);
+            }
+            o[d] = v + a.pos[d];
+        }
+    } else if (tok < ext) {
+        const float* src = a.ctxtok + ((long long)b * a.T + (tok - 1)) * a.D;
+        const float* pe = a.pos + (long long)tok * a.D;
+        float* o = a.out_x + ((long long)b * a.Lx + tok) * a.D;
+        for (int d = threadIdx.x; d < a.D; d += blockDim.x) o[d] = src[d] + pe[d];
+    } else {
+        const bool is_mask = tok >= ext + P;
+        const int pidx = is_mask ? tok - ext - P : tok - ext;
+        const int ph = pidx / g, pw = pidx % g;
+        const int C = is_mask ? a.Cm : a.C;
+        const float* src = (is_mask ? a.mask : a.img) + (long long)bi * C * a.S * a.S;
+        const int kk = C * a.p * a.p;  // <= 64
+        if (threadIdx.x < kk) {
+            const int c = threadIdx.x / (a.p * a.p), r = threadIdx.x % (a.p * a.p);
+            const int i = r / a.p, j = r % a.p;
+            patch[threadIdx.x] = src[((long long)c * a.S + (ph * a.p + i)) * a.S + (pw * a.p + j)];
+        }
+        __syncthreads();
+        const float* w = is_mask ? a.w_msk : a.w_img;
+        const float* bias = is_mask ? a.b_msk : a.b_img;
+        const float* pe = is_mask ? a.pos_m + (long long)pidx * a.D : a.pos + (long long)tok * a.D;
+        float* o = is_mask ? a.out_m + ((long long)b * a.Lm + a.m_off + pidx) * a.D
+                           : a.out_x + ((long long)b * a.Lx + tok) * a.D;
+        for (int d = threadIdx.x; d < a.D; d += blockDim.x) {
+            const float* wr = w + (long long)d * kk;
+            float acc = 0.f;
+            for (int k = 0; k < kk; ++k) acc = fmaf(wr[k], patch[k], acc);
+            o[d] = acc + bias[d] + pe[d];
+        }
+    }
+}
+
+void embed_tokens(const EmbedArgs& a, cudaStream_t s) {
+    PDM_REQUIRE(a.C * a.p * a.p <= 64 && a.Cm * a.p * a.p <= 64, "embed: patch dimension > 64 unsupported");
+    const int g = a.S / a.p;
+    const int ntok = 1 + a.T + g * g + (a.mask ? g * g : 0);
+    dim3 grid(ntok, a.nb);
+    embed_kernel<<<grid, 256, 0, s>>>(a);
+    check_launch("embed");
+}
+
+// ----------------------------------------------------------------------------------------------
+// Head (libs/uvit_t2i.py:477, 499-520): final LayerNorm -> decoder_pred / decoder_pred_mask ->
+// unpatchify -> 3x3 conv (+ tanh on the mask).
+// Kernel 1: one warp per (row, patch, stream); kernel 2: one thread per output pixel.
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) head_token_kernel(HeadArgs a) {
+    const int g = a.S / a.p;
+    const int P = g * g;
+    const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    const int nstream = a.m ? 2 : 1;
+    if (warp >= a.nb * P * nstream) return;
+    const int stream = warp / (a.nb * P);
+    const int rem = warp - stream * a.nb * P;
+    const int b = rem / P, pidx = rem % P;
+    const float* row = stream == 0 ? a.x + ((long long)b * a.Lx + a.x_off + pidx) * a.D
+                                   : a.m + ((long long)b * a.Lm + a.m_off + pidx) * a.D;
+    const bool do_ln = stream == 0 || a.ln_m;
+    const int D = a.D;
+    // pass 1: mean / rstd
+    float mean = 0.f, rstd = 1.f;
+    if (do_ln) {
+        float sum = 0.f;
+        for (int d = lane; d < D; d += 32) sum += row[d];
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        mean = sum / (float)D;
+        float sq = 0.f;
+        for (int d = lane; d < D; d += 32) {
+            const float t = row[d] - mean;
+            sq += t * t;
+        }
+        for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        rstd = rsqrtf(sq / (float)D + 1e-5f);
+    }
+    const int C = stream == 0 ? a.C : a.Cm;
+    const int nout = a.p * a.p * C;
+    const float* W = stream == 0 ? a.w_dec : a.w_decm;
+    const float* bias = stream == 0 ? a.b_dec : a.b_decm;
+    float* dst = (stream == 0 ? a.tmp_img : a.tmp_msk) + (long long)b * C * a.S * a.S;
+    const int ph = pidx / g, pw = pidx % g;
+    for (int o = 0; o < nout; ++o) {
+        const float* wr = W + (long long)o * D;
+        float acc = 0.f;
+        for (int d = lane; d < D; d += 32) {
+            float v = row[d];
+            if (do_ln) v = (v - mean) * rstd * a.ln_w[d] + a.ln_b[d];
+            acc = fmaf(v, wr[d], acc);
+        }
+        for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+        if (lane == 0) {
+            // feature o = (p1 * p + p2) * C + c  ->  pixel (ph*p + p1, pw*p + p2), channel c
+            const int c = o % C, pp = o / C;
+            const int p1 = pp / a.p, p2 = pp % a.p;
+            dst[((long long)c * a.S + ph * a.p + p1) * a.S + pw * a.p + p2] = acc + bias[o];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) conv3x3_kernel(const float* __restrict__ in, const float* __restrict__ w,
+                                                      const float* __restrict__ bias, float* __restrict__ out,
+                                                      int nb, int C, int S, int do_tanh) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)nb * C * S * S;
+    if (idx >= total) return;
+    const int x = (int)(idx % S);
+    const int y = (int)((idx / S) % S);
+    const int co = (int)((idx / ((long long)S * S)) % C);
+    const int b = (int)(idx / ((long long)S * S * C));
+    float acc = bias[co];
+    for (int ci = 0; ci < C; ++ci) {
+        const float* ip = in + ((long long)b * C + ci) * S * S;
+        const float* wp = w + ((long long)co * C + ci) * 9;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            const int yy = y + ky - 1;
+            if (yy < 0 || yy >= S) continue;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int xx = x + kx - 1;
+                if (xx < 0 || xx >= S) continue;
+                acc = fmaf(ip[(long long)yy * S + xx], wp[ky * 3 + kx], acc);
+            }
+        }
+    }
+    out[idx] = do_tanh ? tanhf(acc) : acc;
+}
+
+void head_decode(const HeadArgs& a, cudaStream_t s) {
+    const int g = a.S / a.p;
+    const int P = g * g;
+    const int nwarps = a.nb * P * (a.m ? 2 : 1);
+    head_token_kernel<<<ceil_div(nwarps, 8), 256, 0, s>>>(a);
+    check_launch("head_token");
+    {
+        const long long total = (long long)a.nb * a.C * a.S * a.S;
+        conv3x3_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, s>>>(a.tmp_img, a.w_fin, a.b_fin, a.out_img, a.nb,
+                                                                        a.C, a.S, 0);
+        check_launch("conv3x3_img");
+    }
+    if (a.m) {
+        const long long total = (long long)a.nb * a.Cm * a.S * a.S;
+        conv3x3_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, s>>>(a.tmp_msk, a.w_finm, a.b_finm, a.out_msk,
+                                                                        a.nb, a.Cm, a.S, 1);
+        check_launch("conv3x3_msk");
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// K12: classifier-free guidance on eps and on the mask prediction (train_t2i_discrete.py:429-431),
+// eps -> x0 (dpm_solver_pp.py:316) and one DPM-Solver++ singlestep linear update for both streams
+// (dpm_solver_pp.py:444-456, 529-555, 724-764).  Explicit round-to-nearest intrinsics keep the
+// reference's operation order (no FMA contraction), so with bit-identical scalars the result is
+// bit-identical to the reference arithmetic.
+//   X   = (x_in - sigma * eps) / alpha,   eps = c + s * (c - u)
+//   out = A * x_base + B * X0 [+ C * (X - X0)]          (signs folded into B, C)
+// Algorithmic bytes per element: image reads c,u,x_in,(x_base,X0) writes (X0),out; mask likewise.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ float lin_update(float xb, float x0, float xj, float A, float B, float C, int has_c) {
+    float r = __fadd_rn(__fmul_rn(A, xb), __fmul_rn(B, x0));
+    if (has_c) r = __fadd_rn(r, __fmul_rn(C, __fsub_rn(xj, x0)));
+    return r;
+}
+
+__global__ void __launch_bounds__(256) update_kernel(UpdateArgs a) {
+    const long long n4i = a.n_img >> 2, n4m = a.n_mask >> 2;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n4i + n4m; i += stride) {
+        if (i < n4i) {
+            const float4 c = __ldg(reinterpret_cast<const float4*>(a.eps_c) + i);
+            float4 e = c;
+            if (a.eps_u) {
+                const float4 u = __ldg(reinterpret_cast<const float4*>(a.eps_u) + i);
+                e.x = __fadd_rn(c.x, __fmul_rn(a.scale, __fsub_rn(c.x, u.x)));
+                e.y = __fadd_rn(c.y, __fmul_rn(a.scale, __fsub_rn(c.y, u.y)));
+                e.z = __fadd_rn(c.z, __fmul_rn(a.scale, __fsub_rn(c.z, u.z)));
+                e.w = __fadd_rn(c.w, __fmul_rn(a.scale, __fsub_rn(c.w, u.w)));
+            }
+            const float4 xi = __ldg(reinterpret_cast<const float4*>(a.x_in) + i);
+            float4 X;
+            X.x = __fdiv_rn(__fsub_rn(xi.x, __fmul_rn(a.sigma, e.x)), a.alpha);
+            X.y = __fdiv_rn(__fsub_rn(xi.y, __fmul_rn(a.sigma, e.y)), a.alpha);
+            X.z = __fdiv_rn(__fsub_rn(xi.z, __fmul_rn(a.sigma, e.z)), a.alpha);
+            X.w = __fdiv_rn(__fsub_rn(xi.w, __fmul_rn(a.sigma, e.w)), a.alpha);
+            float4 x0, xb;
+            if (a.stage == 0) {
+                x0 = X;
+                xb = xi;  // x_in == x_base at stage 0
+                reinterpret_cast<float4*>(a.X0)[i] = X;
+            } else {
+                x0 = reinterpret_cast<const float4*>(a.X0)[i];
+                xb = __ldg(reinterpret_cast<const float4*>(a.x_base) + i);
+            }
+            float4 o;
+            o.x = lin_update(xb.x, x0.x, X.x, a.A, a.B_img, a.C_img, a.has_c);
+            o.y = lin_update(xb.y, x0.y, X.y, a.A, a.B_img, a.C_img, a.has_c);
+            o.z = lin_update(xb.z, x0.z, X.z, a.A, a.B_img, a.C_img, a.has_c);
+            o.w = lin_update(xb.w, x0.w, X.w, a.A, a.B_img, a.C_img, a.has_c);
+            reinterpret_cast<float4*>(a.x_out)[i] = o;
+        } else {
+            const long long j = i - n4i;
+            const float4 c = __ldg(reinterpret_cast<const float4*>(a.pm_c) + j);
+            float4 P = c;
+            if (a.pm_u) {
+                const float4 u = __ldg(reinterpret_cast<const float4*>(a.pm_u) + j);
+                P.x = __fadd_rn(c.x, __fmul_rn(a.scale, __fsub_rn(c.x, u.x)));
+                P.y = __fadd_rn(c.y, __fmul_rn(a.scale, __fsub_rn(c.y, u.y)));
+                P.z = __fadd_rn(c.z, __fmul_rn(a.scale, __fsub_rn(c.z, u.z)));
+                P.w = __fadd_rn(c.w, __fmul_rn(a.scale, __fsub_rn(c.w, u.w)));
+            }
+            float4 p0;
+            if (a.stage == 0) {
+                p0 = P;
+                reinterpret_cast<float4*>(a.P0)[j] = P;
+            } else {
+                p0 = reinterpret_cast<const float4*>(a.P0)[j];
+            }
+            const float4 mb = __ldg(reinterpret_cast<const float4*>(a.m_base) + j);
+            float4 o;
+            o.x = lin_update(mb.x, p0.x, P.x, a.A, a.B_msk, a.C_msk, a.has_c);
+            o.y = lin_update(mb.y, p0.y, P.y, a.A, a.B_msk, a.C_msk, a.has_c);
+            o.z = lin_update(mb.z, p0.z, P.z, a.A, a.B_msk, a.C_msk, a.has_c);
+            o.w = lin_update(mb.w, p0.w, P.w, a.A, a.B_msk, a.C_msk, a.has_c);
+            reinterpret_cast<float4*>(a.m_out)[j] = o;
+        }
+    }
+}
+
+void cfg_solver_update(const UpdateArgs& a, cudaStream_t s) {
+    PDM_REQUIRE(a.n_img % 4 == 0 && a.n_mask % 4 == 0, "cfg_update: element counts must be multiples of 4");
+    PDM_REQUIRE(a.n_mask == 0 || (a.pm_c && a.m_base && a.P0 && a.m_out), "cfg_update: mask pointers missing");
+    const long long n4 = (a.n_img + a.n_mask) / 4;
+    const int grid = (int)std::max<long long>(1, std::min<long long>(ceil_div_ll(n4, 256), 148 * 8));
+    update_kernel<<<grid, 256, 0, s>>>(a);
+    check_launch("cfg_solver_update");
+}
+
+// ----------------------------------------------------------------------------------------------
+// analog-bit codec (utils.py:475-518): MSB first.
+// ----------------------------------------------------------------------------------------------
+__global__ void bits2int_kernel(const float* __restrict__ pm, int32_t* __restrict__ labels, int B, int nbits, int hw) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)B * hw) return;
+    const int b = (int)(idx / hw), p = (int)(idx % hw);
+    int v = 0;
+    for (int i = 0; i < nbits; ++i) v = (v << 1) | (pm[((long long)b * nbits + i) * hw + p] > 0.f ? 1 : 0);
+    labels[idx] = v;
+}
+__global__ void int2bits_kernel(const int32_t* __restrict__ ids, float* __restrict__ bits, int B, int nbits, int hw) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)B * nbits * hw) return;
+    const int p = (int)(idx % hw);
+    const int i = (int)((idx / hw) % nbits);
+    const int b = (int)(idx / ((long long)hw * nbits));
+    const int bit = (ids[(long long)b * hw + p] >> (nbits - 1 - i)) & 1;
+    bits[idx] = bit ? 1.f : -1.f;
+}
+void bits2int(const float* pm, int32_t* labels, int B, int nbits, int hw, cudaStream_t s) {
+    bits2int_kernel<<<(unsigned)ceil_div_ll((long long)B * hw, 256), 256, 0, s>>>(pm, labels, B, nbits, hw);
+    check_launch("bits2int");
+}
+void int2bits(const int32_t* ids, float* bits, int B, int nbits, int hw, cudaStream_t s) {
+    int2bits_kernel<<<(unsigned)ceil_div_ll((long long)B * nbits * hw, 256), 256, 0, s>>>(ids, bits, B, nbits, hw);
+    check_launch("int2bits");
+}
+
+}  // namespace pdm

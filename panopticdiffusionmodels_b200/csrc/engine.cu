@@ -1,0 +1,939 @@
+// Engine: owns parameters + workspace, orchestrates the U-ViT forward (libs/uvit_t2i.py:378-525) and the
+// device-resident DPM-Solver++ loop (dpm_solver_pp.py:1018-1044 driven by train_t2i_discrete.py:387-439),
+// and exports the C ABI declared in include/pdm.h.
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/pdm.h"
+#include "common.cuh"
+
+namespace pdm {
+
+void clear_tmap_cache();
+
+namespace {
+
+thread_local std::string g_last_error;
+
+struct Param {
+    std::vector<int64_t> shape;
+    size_t n = 0;
+    float* d32 = nullptr;
+    bf16* d16 = nullptr;
+    bool set = false;
+    bool gemm_weight = false;  // needs a bf16 copy
+};
+
+struct LinearW {
+    const float* w32 = nullptr;
+    const bf16* w16 = nullptr;
+    const float* b = nullptr;
+    int N = 0, K = 0;
+};
+
+struct BlockW {
+    const float *n1w = nullptr, *n1b = nullptr, *n2w = nullptr, *n2b = nullptr;
+    LinearW qkv, proj, fc1, fc2, skip;
+    bool has_skip = false;
+};
+
+struct Arena {
+    uint8_t* base = nullptr;
+    size_t cap = 0, off = 0;
+    bool dry = true;
+    void* take(size_t bytes) {
+        const size_t a = (off + 255) & ~size_t(255);
+        off = a + bytes;
+        return dry ? nullptr : base + a;
+    }
+};
+
+struct Workspace {
+    int nb = 0, prec = -1;
+    bool with_mask = false;
+    uint8_t* slab = nullptr;
+    size_t bytes = 0;
+    // network
+    float* x = nullptr;       // [nb, L1, D] residual stream (image stream / single stream)
+    float* mx = nullptr;      // [nb, L2, D] two-stream mask-stream residual
+    void* h = nullptr;        // LN out            [R, D]   act
+    void* qkv = nullptr;      //                   [R, 3D]  act
+    void* ao = nullptr;       // attention out     [R, D]   act
+    void* u = nullptr;        // MLP hidden        [R, 4D]  act
+    void* xb = nullptr;       // act copy of x     [R1, D]
+    void* mxb = nullptr;      // act copy of mx    [R2, D]
+    std::vector<void*> skipx; // [depth/2] [R1, D] act
+    std::vector<void*> skipm; // [depth/2] [R2, D] act
+    float* ctx_all = nullptr; // [nb, T, clip] fp32
+    void* ctx_act = nullptr;  // act copy of ctx_all (bf16 mode)
+    float* ctxtok = nullptr;  // [nb, T, D]
+    float* tmp_img = nullptr; // [nb, C, S, S]
+    float* tmp_msk = nullptr; // [nb, Cm, S, S]
+    // sampler state
+    float *xbase = nullptr, *xin = nullptr, *X0 = nullptr;
+    float *mbase = nullptr, *min_ = nullptr, *P0 = nullptr;
+    float *nz = nullptr, *ny = nullptr;
+};
+
+struct GraphEntry {
+    cudaGraphExec_t exec = nullptr;
+    std::vector<float> plan;
+    float scale = 0.f;
+    int B = 0, prec = 0;
+    bool has_mask = false, cfg = false;
+    const Workspace* ws = nullptr;
+    long long n_kernels = 0;
+};
+
+struct ProfEvent {
+    std::string name;
+    cudaEvent_t a, b;
+};
+
+}  // namespace
+
+}  // namespace pdm
+
+using namespace pdm;
+
+struct pdm_engine {
+    pdm_config cfg;
+    int D, H, S, p, g, P, T, ext, C, Cm, depth, L1, L2;
+    bool two;  // separate topology
+    std::map<std::string, Param> params;
+    bool finalized = false;
+    std::vector<BlockW> in_b, out_b, in_bm, out_bm;
+    BlockW mid_b, mid_bm;
+    std::vector<LinearW> zc;  // zc[li] = zero_convs[2*li+1]
+    LinearW ctx_lin;
+    float* freqs = nullptr;
+    std::vector<std::unique_ptr<Workspace>> spaces;
+    std::vector<GraphEntry> graphs;
+    bool profiling = false;
+    std::vector<ProfEvent> prof;
+
+    ~pdm_engine() {
+        for (auto& kv : params) {
+            if (kv.second.d32) cudaFree(kv.second.d32);
+            if (kv.second.d16) cudaFree(kv.second.d16);
+        }
+        if (freqs) cudaFree(freqs);
+        for (auto& g : graphs)
+            if (g.exec) cudaGraphExecDestroy(g.exec);
+        for (auto& w : spaces)
+            if (w->slab) cudaFree(w->slab);
+        for (auto& e : prof) {
+            cudaEventDestroy(e.a);
+            cudaEventDestroy(e.b);
+        }
+    }
+
+    // ------------------------------------------------------------------ parameters
+    void expect(const std::string& key, std::vector<int64_t> shape, bool gemm_weight = false) {
+        Param p;
+        p.shape = shape;
+        p.n = 1;
+        for (auto s : shape) p.n *= (size_t)s;
+        p.gemm_weight = gemm_weight;
+        params[key] = p;
+    }
+    void expect_block(const std::string& pre, bool skip) {
+        const int64_t d = D;
+        expect(pre + "norm1.weight", {d});
+        expect(pre + "norm1.bias", {d});
+        expect(pre + "attn.qkv.weight", {3 * d, d}, true);
+        expect(pre + "attn.proj.weight", {d, d}, true);
+        expect(pre + "attn.proj.bias", {d});
+        expect(pre + "norm2.weight", {d});
+        expect(pre + "norm2.bias", {d});
+        expect(pre + "mlp.fc1.weight", {cfg.mlp_ratio * d, d}, true);
+        expect(pre + "mlp.fc1.bias", {cfg.mlp_ratio * d});
+        expect(pre + "mlp.fc2.weight", {d, cfg.mlp_ratio * d}, true);
+        expect(pre + "mlp.fc2.bias", {d});
+        if (skip) {
+            expect(pre + "skip_linear.weight", {d, 2 * d}, true);
+            expect(pre + "skip_linear.bias", {d});
+        }
+    }
+    void declare_params() {
+        const int64_t d = D;
+        const int64_t ntok = ext + P + ((cfg.enable_panoptic && !two) ? P : 0);
+        expect("pos_embed", {1, ntok, d});
+        expect("patch_embed.proj.weight", {d, C, p, p});
+        expect("patch_embed.proj.bias", {d});
+        expect("context_embed.weight", {d, cfg.clip_dim}, true);
+        expect("context_embed.bias", {d});
+        for (int i = 0; i < depth / 2; ++i) expect_block("in_blocks." + std::to_string(i) + ".", false);
+        expect_block("mid_block.", false);
+        for (int i = 0; i < depth / 2; ++i) expect_block("out_blocks." + std::to_string(i) + ".", true);
+        expect("norm.weight", {d});
+        expect("norm.bias", {d});
+        expect("decoder_pred.weight", {(int64_t)p * p * C, d});
+        expect("decoder_pred.bias", {(int64_t)p * p * C});
+        expect("final_layer.weight", {C, C, 3, 3});
+        expect("final_layer.bias", {C});
+        if (cfg.enable_panoptic) {
+            expect("mask_embed.proj.weight", {d, Cm, p, p});
+            expect("mask_embed.proj.bias", {d});
+            expect("decoder_pred_mask.weight", {(int64_t)p * p * Cm, d});
+            expect("decoder_pred_mask.bias", {(int64_t)p * p * Cm});
+            expect("final_layer_mask.weight", {Cm, Cm, 3, 3});
+            expect("final_layer_mask.bias", {Cm});
+        }
+        if (two) {
+            expect("pos_embed_mask", {1, P, d});
+            for (int i = 0; i < depth / 2; ++i) expect_block("in_blocks_mask." + std::to_string(i) + ".", false);
+            expect_block("mid_block_mask.", false);
+            for (int i = 0; i < depth / 2; ++i) expect_block("out_blocks_mask." + std::to_string(i) + ".", true);
+            for (int li = 0; li <= depth; ++li) {
+                const std::string pre = "zero_convs." + std::to_string(2 * li + 1) + ".conv.";
+                expect(pre + "weight", {d, d, 1}, true);
+                expect(pre + "bias", {d});
+            }
+        }
+    }
+    bool ignorable(const std::string& key) const {
+        if (key.rfind("mask_embed_0.", 0) == 0) return cfg.enable_panoptic;
+        if (two && key.rfind("zero_convs.", 0) == 0) {
+            const int idx = atoi(key.c_str() + 11);
+            return idx >= 0 && idx < 2 * depth + 2 && (idx % 2 == 0);
+        }
+        return false;
+    }
+    void set_param(const std::string& key, const void* dev, const int64_t* shape, int ndim, cudaStream_t s) {
+        if (key == "__timestep_freqs__") {
+            // optional override of the sinusoidal frequency table (host layer uploads the table built with the
+            // reference's own float32 torch ops, libs/uvit_t2i.py:30-33)
+            PDM_REQUIRE(ndim == 1 && shape[0] == D / 2, "__timestep_freqs__ must have shape (D/2,)");
+            PDM_CHECK_CUDA(cudaMemcpyAsync(freqs, dev, (D / 2) * sizeof(float), cudaMemcpyDeviceToDevice, s));
+            return;
+        }
+        if (ignorable(key)) return;
+        auto it = params.find(key);
+        PDM_REQUIRE(it != params.end(), "unexpected state_dict key '" + key + "'");
+        Param& p = it->second;
+        bool ok = (int)p.shape.size() == ndim;
+        for (int i = 0; ok && i < ndim; ++i) ok = p.shape[i] == shape[i];
+        if (!ok) {
+            std::string want, got;
+            for (auto v : p.shape) want += std::to_string(v) + ",";
+            for (int i = 0; i < ndim; ++i) got += std::to_string(shape[i]) + ",";
+            throw Error("size mismatch for " + key + ": expected (" + want + ") got (" + got + ")");
+        }
+        if (!p.d32) PDM_CHECK_CUDA(cudaMalloc(&p.d32, p.n * sizeof(float)));
+        PDM_CHECK_CUDA(cudaMemcpyAsync(p.d32, dev, p.n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        if (p.gemm_weight) {
+            PDM_REQUIRE(p.n % 4 == 0, "weight size must be a multiple of 4: " + key);
+            if (!p.d16) PDM_CHECK_CUDA(cudaMalloc(&p.d16, p.n * sizeof(bf16)));
+            convert_f32_bf16(p.d32, p.d16, (long long)p.n, s);
+        }
+        p.set = true;
+        // cached graphs bake nothing about weights (pointers are stable), so they stay valid.
+    }
+    LinearW lin(const std::string& w, const std::string& b, int N, int K) {
+        LinearW l;
+        l.w32 = params.at(w).d32;
+        l.w16 = params.at(w).d16;
+        l.b = b.empty() ? nullptr : params.at(b).d32;
+        l.N = N;
+        l.K = K;
+        return l;
+    }
+    BlockW block(const std::string& pre, bool skip) {
+        BlockW b;
+        b.n1w = params.at(pre + "norm1.weight").d32;
+        b.n1b = params.at(pre + "norm1.bias").d32;
+        b.n2w = params.at(pre + "norm2.weight").d32;
+        b.n2b = params.at(pre + "norm2.bias").d32;
+        b.qkv = lin(pre + "attn.qkv.weight", "", 3 * D, D);
+        b.proj = lin(pre + "attn.proj.weight", pre + "attn.proj.bias", D, D);
+        b.fc1 = lin(pre + "mlp.fc1.weight", pre + "mlp.fc1.bias", cfg.mlp_ratio * D, D);
+        b.fc2 = lin(pre + "mlp.fc2.weight", pre + "mlp.fc2.bias", D, cfg.mlp_ratio * D);
+        b.has_skip = skip;
+        if (skip) b.skip = lin(pre + "skip_linear.weight", pre + "skip_linear.bias", D, 2 * D);
+        return b;
+    }
+    void finalize(cudaStream_t s) {
+        std::string missing;
+        int nmiss = 0;
+        for (auto& kv : params)
+            if (!kv.second.set) {
+                if (nmiss < 8) missing += kv.first + " ";
+                ++nmiss;
+            }
+        PDM_REQUIRE(nmiss == 0, "missing " + std::to_string(nmiss) + " state_dict keys: " + missing);
+        in_b.clear(); out_b.clear(); in_bm.clear(); out_bm.clear(); zc.clear();
+        for (int i = 0; i < depth / 2; ++i) in_b.push_back(block("in_blocks." + std::to_string(i) + ".", false));
+        mid_b = block("mid_block.", false);
+        for (int i = 0; i < depth / 2; ++i) out_b.push_back(block("out_blocks." + std::to_string(i) + ".", true));
+        if (two) {
+            for (int i = 0; i < depth / 2; ++i)
+                in_bm.push_back(block("in_blocks_mask." + std::to_string(i) + ".", false));
+            mid_bm = block("mid_block_mask.", false);
+            for (int i = 0; i < depth / 2; ++i)
+                out_bm.push_back(block("out_blocks_mask." + std::to_string(i) + ".", true));
+            for (int li = 0; li <= depth; ++li) {
+                const std::string pre = "zero_convs." + std::to_string(2 * li + 1) + ".conv.";
+                zc.push_back(lin(pre + "weight", pre + "bias", D, D));
+            }
+        }
+        ctx_lin = lin("context_embed.weight", "context_embed.bias", D, cfg.clip_dim);
+        PDM_CHECK_CUDA(cudaStreamSynchronize(s));
+        finalized = true;
+    }
+
+    // ------------------------------------------------------------------ workspace
+    void carve(Workspace& w, Arena& a) const {
+        const size_t act = w.prec == PDM_PREC_BF16 ? 2 : 4;
+        const bool two_m = two && w.with_mask;
+        const size_t Lx = (size_t)(two_m ? L1 : (w.with_mask ? L2 : L1));
+        const size_t R1 = (size_t)w.nb * Lx;
+        const size_t R2 = two_m ? (size_t)w.nb * L2 : 0;
+        const size_t R = std::max(R1, R2);
+        const size_t d = D;
+        w.x = (float*)a.take(R1 * d * 4);
+        w.mx = two_m ? (float*)a.take(R2 * d * 4) : nullptr;
+        w.h = a.take(R * d * act);
+        w.qkv = a.take(R * 3 * d * act);
+        w.ao = a.take(R * d * act);
+        w.u = a.take(R * cfg.mlp_ratio * d * act);
+        w.xb = a.take(R1 * d * act);
+        w.mxb = two_m ? a.take(R2 * d * act) : nullptr;
+        w.skipx.resize(depth / 2);
+        w.skipm.resize(two_m ? depth / 2 : 0);
+        for (auto& sp : w.skipx) sp = a.take(R1 * d * act);
+        for (auto& sp : w.skipm) sp = a.take(R2 * d * act);
+        w.ctx_all = (float*)a.take((size_t)w.nb * T * cfg.clip_dim * 4);
+        w.ctx_act = w.prec == PDM_PREC_BF16 ? a.take((size_t)w.nb * T * cfg.clip_dim * 2) : nullptr;
+        w.ctxtok = (float*)a.take((size_t)w.nb * T * d * 4);
+        const size_t img = (size_t)C * S * S, msk = (size_t)Cm * S * S;
+        w.tmp_img = (float*)a.take(w.nb * img * 4);
+        w.tmp_msk = (float*)a.take(w.nb * msk * 4);
+        w.xbase = (float*)a.take(w.nb * img * 4);
+        w.xin = (float*)a.take(w.nb * img * 4);
+        w.X0 = (float*)a.take(w.nb * img * 4);
+        w.mbase = (float*)a.take(w.nb * msk * 4);
+        w.min_ = (float*)a.take(w.nb * msk * 4);
+        w.P0 = (float*)a.take(w.nb * msk * 4);
+        w.nz = (float*)a.take(w.nb * img * 4);
+        w.ny = (float*)a.take(w.nb * msk * 4);
+    }
+    size_t workspace_bytes(int nb, int prec, bool with_mask) const {
+        Workspace w;
+        w.nb = nb;
+        w.prec = prec;
+        w.with_mask = with_mask;
+        Arena a;
+        carve(w, a);
+        return a.off + 256;
+    }
+    Workspace& workspace(int nb, int prec, bool with_mask) {
+        for (auto& w : spaces)
+            if (w->nb == nb && w->prec == prec && w->with_mask == with_mask) return *w;
+        // keep at most 4 workspaces alive; drop the oldest (and any graph that references it)
+        if (spaces.size() >= 4) {
+            PDM_CHECK_CUDA(cudaDeviceSynchronize());
+            Workspace* old = spaces.front().get();
+            for (size_t i = 0; i < graphs.size();) {
+                if (graphs[i].ws == old) {
+                    cudaGraphExecDestroy(graphs[i].exec);
+                    graphs.erase(graphs.begin() + i);
+                } else {
+                    ++i;
+                }
+            }
+            cudaFree(old->slab);
+            spaces.erase(spaces.begin());
+            clear_tmap_cache();
+        }
+        std::unique_ptr<Workspace> w(new Workspace());
+        w->nb = nb;
+        w->prec = prec;
+        w->with_mask = with_mask;
+        w->bytes = workspace_bytes(nb, prec, with_mask);
+        PDM_CHECK_CUDA(cudaMalloc(&w->slab, w->bytes));
+        Arena a;
+        a.base = w->slab;
+        a.cap = w->bytes;
+        a.dry = false;
+        carve(*w, a);
+        spaces.push_back(std::move(w));
+        return *spaces.back();
+    }
+
+    // ------------------------------------------------------------------ profiling
+    struct Scope {
+        pdm_engine* e;
+        int idx = -1;
+        cudaStream_t s;
+        Scope(pdm_engine* e_, const char* name, cudaStream_t s_) : e(e_), s(s_) {
+            if (!e->profiling) return;
+            ProfEvent ev;
+            ev.name = name;
+            cudaEventCreate(&ev.a);
+            cudaEventCreate(&ev.b);
+            cudaEventRecord(ev.a, s);
+            e->prof.push_back(ev);
+            idx = (int)e->prof.size() - 1;
+        }
+        ~Scope() {
+            if (idx >= 0) cudaEventRecord(e->prof[idx].b, s);
+        }
+    };
+
+    // ------------------------------------------------------------------ network
+    void gemm(const GemmProblem& g, int prec, cudaStream_t s) {
+        if (prec == PDM_PREC_BF16)
+            gemm_tc_bf16(g, s);
+        else
+            gemm_simt_f32(g, s);
+    }
+
+    // one transformer block on a flat [R, D] residual stream (libs/uvit_t2i.py:177-226)
+    void run_block(const BlockW& w, Workspace& ws, float* x, int nb, int Lx, const void* skipA1, const void* skipA2,
+                   void* out2, int prec, cudaStream_t s) {
+        const int R = nb * Lx;
+        const bool b16 = prec == PDM_PREC_BF16;
+        if (w.has_skip) {
+            Scope sc(this, "gemm_skip", s);
+            GemmProblem g;
+            g.A1 = skipA1; g.K1 = D; g.A2 = skipA2; g.K2 = D;
+            g.W32 = w.skip.w32; g.W16 = w.skip.w16; g.bias = w.skip.b; g.N = D;
+            g.nb = 1; g.Lr = R; g.out32 = x;
+            gemm(g, prec, s);
+        }
+        {
+            Scope sc(this, "layernorm", s);
+            layernorm(x, w.n1w, w.n1b, ws.h, b16, R, D, s);
+        }
+        {
+            Scope sc(this, "gemm_qkv", s);
+            GemmProblem g;
+            g.A1 = ws.h; g.K1 = D; g.W32 = w.qkv.w32; g.W16 = w.qkv.w16; g.N = 3 * D;
+            g.nb = 1; g.Lr = R; g.out2 = ws.qkv;
+            gemm(g, prec, s);
+        }
+        {
+            Scope sc(this, "attention", s);
+            if (b16)
+                attention_tc_bf16((const bf16*)ws.qkv, (bf16*)ws.ao, nb, Lx, H, s);
+            else
+                attention_simt(ws.qkv, ws.ao, nb, Lx, H, false, s);
+        }
+        {
+            Scope sc(this, "gemm_proj", s);
+            GemmProblem g;
+            g.A1 = ws.ao; g.K1 = D; g.W32 = w.proj.w32; g.W16 = w.proj.w16; g.bias = w.proj.b; g.N = D;
+            g.nb = 1; g.Lr = R; g.resid = x; g.out32 = x;
+            gemm(g, prec, s);
+        }
+        {
+            Scope sc(this, "layernorm", s);
+            layernorm(x, w.n2w, w.n2b, ws.h, b16, R, D, s);
+        }
+        {
+            Scope sc(this, "gemm_fc1", s);
+            GemmProblem g;
+            g.A1 = ws.h; g.K1 = D; g.W32 = w.fc1.w32; g.W16 = w.fc1.w16; g.bias = w.fc1.b; g.N = w.fc1.N;
+            g.nb = 1; g.Lr = R; g.out2 = ws.u; g.gelu = true;
+            gemm(g, prec, s);
+        }
+        {
+            Scope sc(this, "gemm_fc2", s);
+            GemmProblem g;
+            g.A1 = ws.u; g.K1 = w.fc2.K; g.W32 = w.fc2.w32; g.W16 = w.fc2.w16; g.bias = w.fc2.b; g.N = D;
+            g.nb = 1; g.Lr = R; g.resid = x; g.out32 = x; g.out2 = out2;
+            gemm(g, prec, s);
+        }
+    }
+
+    // x += zero_conv(mx_act[:, :L1])  (libs/uvit_t2i.py:432-436); also emits the activation copy of x
+    void run_zero_conv(const LinearW& z, Workspace& ws, const void* mx_act, void* out2, int nb, int prec,
+                       cudaStream_t s) {
+        Scope sc(this, "gemm_zeroconv", s);
+        GemmProblem g;
+        g.A1 = mx_act; g.K1 = D; g.a1_bs = L2;
+        g.W32 = z.w32; g.W16 = z.w16; g.bias = z.b; g.N = D;
+        g.nb = nb; g.Lr = L1;
+        g.resid = ws.x; g.resid_bs = L1; g.out32 = ws.x; g.out32_bs = L1; g.out2 = out2; g.out2_bs = L1;
+        gemm(g, prec, s);
+    }
+
+    void compute_ctxtok(Workspace& ws, int nb, int prec, cudaStream_t s) {
+        Scope sc(this, "context_embed", s);
+        const void* a = ws.ctx_all;
+        if (prec == PDM_PREC_BF16) {
+            convert_f32_bf16(ws.ctx_all, (bf16*)ws.ctx_act, (long long)nb * T * cfg.clip_dim, s);
+            a = ws.ctx_act;
+        }
+        GemmProblem g;
+        g.A1 = a; g.K1 = cfg.clip_dim;
+        g.W32 = ctx_lin.w32; g.W16 = ctx_lin.w16; g.bias = ctx_lin.b; g.N = D;
+        g.nb = 1; g.Lr = nb * T; g.out32 = ws.ctxtok;
+        gemm(g, prec, s);
+    }
+
+    // ws.ctxtok must be ready.  img/mask: [Bx, ...] inputs, evaluated for nb rows (row b uses input b % Bx).
+    void forward(Workspace& ws, const float* img, const float* mask, int Bx, int nb, const float* t_dev, float t_scalar,
+                 float* out_noise, float* out_mask, int prec, cudaStream_t s) {
+        const bool with_mask = mask != nullptr;
+        const bool two_m = two && with_mask;
+        const bool b16 = prec == PDM_PREC_BF16;
+        const int Lx = two_m ? L1 : (with_mask ? L2 : L1);
+        {
+            Scope sc(this, "embed", s);
+            EmbedArgs a;
+            a.img = img; a.mask = mask; a.Bx = Bx; a.nb = nb; a.t_dev = t_dev; a.t_scalar = t_scalar;
+            a.freqs = freqs; a.ctxtok = ws.ctxtok;
+            a.w_img = params.at("patch_embed.proj.weight").d32;
+            a.b_img = params.at("patch_embed.proj.bias").d32;
+            a.w_msk = with_mask ? params.at("mask_embed.proj.weight").d32 : nullptr;
+            a.b_msk = with_mask ? params.at("mask_embed.proj.bias").d32 : nullptr;
+            a.pos = params.at("pos_embed").d32;
+            a.pos_m = two_m ? params.at("pos_embed_mask").d32 : a.pos + (size_t)(ext + P) * D;
+            a.out_x = ws.x; a.Lx = Lx;
+            a.out_m = two_m ? ws.mx : ws.x; a.Lm = two_m ? L2 : Lx; a.m_off = ext + P;
+            a.C = C; a.Cm = Cm; a.S = S; a.p = p; a.D = D; a.T = T;
+            embed_tokens(a, s);
+        }
+        const int half = depth / 2;
+        const size_t actsz = b16 ? 2 : 4;
+        if (!two_m) {
+            for (int i = 0; i < half; ++i) run_block(in_b[i], ws, ws.x, nb, Lx, nullptr, nullptr, ws.skipx[i], prec, s);
+            run_block(mid_b, ws, ws.x, nb, Lx, nullptr, nullptr, ws.xb, prec, s);
+            for (int j = 0; j < half; ++j)
+                run_block(out_b[j], ws, ws.x, nb, Lx, ws.xb, ws.skipx[half - 1 - j], j + 1 < half ? ws.xb : nullptr, prec, s);
+        } else {
+            int li = 0;
+            for (int i = 0; i < half; ++i, ++li) {
+                {
+                    Scope sc(this, "concat", s);
+                    copy_rows(ws.mx, L2, ws.x, L1, L1, nb, D * 4, s);
+                }
+                run_block(in_b[i], ws, ws.x, nb, L1, nullptr, nullptr, nullptr, prec, s);
+                run_block(in_bm[i], ws, ws.mx, nb, L2, nullptr, nullptr, ws.skipm[i], prec, s);
+                run_zero_conv(zc[li], ws, ws.skipm[i], ws.skipx[i], nb, prec, s);
+            }
+            {
+                Scope sc(this, "concat", s);
+                copy_rows(ws.mx, L2, ws.x, L1, L1, nb, D * 4, s);
+            }
+            run_block(mid_b, ws, ws.x, nb, L1, nullptr, nullptr, nullptr, prec, s);
+            run_block(mid_bm, ws, ws.mx, nb, L2, nullptr, nullptr, ws.mxb, prec, s);
+            run_zero_conv(zc[li], ws, ws.mxb, ws.xb, nb, prec, s);
+            ++li;
+            for (int j = 0; j < half; ++j, ++li) {
+                {
+                    Scope sc(this, "concat", s);
+                    copy_rows(ws.mx, L2, ws.x, L1, L1, nb, D * 4, s);
+                    copy_rows(ws.mxb, L2, ws.xb, L1, L1, nb, (int)(D * actsz), s);
+                }
+                run_block(out_b[j], ws, ws.x, nb, L1, ws.xb, ws.skipx[half - 1 - j], nullptr, prec, s);
+                run_block(out_bm[j], ws, ws.mx, nb, L2, ws.mxb, ws.skipm[half - 1 - j], ws.mxb, prec, s);
+                run_zero_conv(zc[li], ws, ws.mxb, ws.xb, nb, prec, s);
+            }
+        }
+        {
+            Scope sc(this, "head", s);
+            HeadArgs a;
+            a.x = ws.x; a.Lx = Lx; a.x_off = ext;
+            a.m = with_mask ? (two_m ? ws.mx : ws.x) : nullptr;
+            a.Lm = two_m ? L2 : Lx; a.m_off = ext + P; a.ln_m = !two_m;
+            a.ln_w = params.at("norm.weight").d32; a.ln_b = params.at("norm.bias").d32;
+            a.w_dec = params.at("decoder_pred.weight").d32; a.b_dec = params.at("decoder_pred.bias").d32;
+            a.w_fin = params.at("final_layer.weight").d32; a.b_fin = params.at("final_layer.bias").d32;
+            a.w_decm = a.b_decm = a.w_finm = a.b_finm = nullptr;
+            if (with_mask) {
+                a.w_decm = params.at("decoder_pred_mask.weight").d32; a.b_decm = params.at("decoder_pred_mask.bias").d32;
+                a.w_finm = params.at("final_layer_mask.weight").d32; a.b_finm = params.at("final_layer_mask.bias").d32;
+            }
+            a.tmp_img = ws.tmp_img; a.tmp_msk = ws.tmp_msk; a.out_img = out_noise; a.out_msk = out_mask;
+            a.nb = nb; a.C = C; a.Cm = Cm; a.S = S; a.p = p; a.D = D;
+            head_decode(a, s);
+        }
+    }
+
+    // ------------------------------------------------------------------ sampler
+    void enqueue_loop(Workspace& ws, const float* plan, int n_evals, int B, bool has_mask, bool cfg_on, float scale,
+                      int prec, cudaStream_t s) {
+        const int nb = cfg_on ? 2 * B : B;
+        const long long n_img = (long long)B * C * S * S, n_msk = has_mask ? (long long)B * Cm * S * S : 0;
+        compute_ctxtok(ws, nb, prec, s);
+        for (int k = 0; k < n_evals; ++k) {
+            const float* r = plan + (size_t)k * PDM_PLAN_STRIDE;
+            const int stage = (int)r[8];
+            const bool last = r[10] != 0.f;
+            const float* xin = stage == 0 ? ws.xbase : ws.xin;
+            const float* min_ = has_mask ? (stage == 0 ? ws.mbase : ws.min_) : nullptr;
+            forward(ws, xin, min_, B, nb, nullptr, r[0], ws.nz, has_mask ? ws.ny : nullptr, prec, s);
+            Scope sc(this, "cfg_solver_update", s);
+            UpdateArgs u;
+            u.eps_c = ws.nz; u.eps_u = cfg_on ? ws.nz + n_img : nullptr;
+            u.pm_c = has_mask ? ws.ny : nullptr; u.pm_u = (has_mask && cfg_on) ? ws.ny + n_msk : nullptr;
+            u.x_in = xin; u.x_base = ws.xbase; u.X0 = ws.X0; u.x_out = last ? ws.xbase : ws.xin;
+            u.m_base = ws.mbase; u.P0 = ws.P0; u.m_out = last ? ws.mbase : ws.min_;
+            u.alpha = r[1]; u.sigma = r[2]; u.A = r[3]; u.B_img = r[4]; u.C_img = r[5]; u.B_msk = r[6]; u.C_msk = r[7];
+            u.scale = scale; u.stage = stage; u.has_c = r[9] != 0.f ? 1 : 0;
+            u.n_img = n_img; u.n_mask = n_msk;
+            cfg_solver_update(u, s);
+        }
+    }
+
+    void sample(const float* plan, int n_evals, const float* z_init, const float* mask_init, const float* ctx,
+                const float* empty_ctx, float scale, float* out_z, float* out_pm, int B, int prec, bool use_graph,
+                cudaStream_t s) {
+        PDM_REQUIRE(finalized, "parameters not finalized");
+        PDM_REQUIRE(n_evals > 0 && B > 0, "bad sample arguments");
+        const bool has_mask = mask_init != nullptr;
+        PDM_REQUIRE(!has_mask || cfg.enable_panoptic, "model built with enable_panoptic=False cannot take a mask");
+        PDM_REQUIRE(!has_mask || out_pm, "out_pred_mask required");
+        const bool cfg_on = empty_ctx != nullptr;
+        const int nb = cfg_on ? 2 * B : B;
+        Workspace& ws = workspace(nb, prec, has_mask);
+        const size_t img = (size_t)B * C * S * S * 4, msk = (size_t)B * Cm * S * S * 4;
+        const size_t ctxb = (size_t)B * T * cfg.clip_dim * 4;
+        PDM_CHECK_CUDA(cudaMemcpyAsync(ws.xbase, z_init, img, cudaMemcpyDeviceToDevice, s));
+        if (has_mask) PDM_CHECK_CUDA(cudaMemcpyAsync(ws.mbase, mask_init, msk, cudaMemcpyDeviceToDevice, s));
+        PDM_CHECK_CUDA(cudaMemcpyAsync(ws.ctx_all, ctx, ctxb, cudaMemcpyDeviceToDevice, s));
+        if (cfg_on)
+            copy_rows(ws.ctx_all + (size_t)B * T * cfg.clip_dim, T, empty_ctx, 0, T, B, cfg.clip_dim * 4, s);
+        if (!use_graph || profiling) {
+            enqueue_loop(ws, plan, n_evals, B, has_mask, cfg_on, scale, prec, s);
+        } else {
+            GraphEntry* hit = nullptr;
+            for (auto& g : graphs) {
+                if (g.ws == &ws && g.B == B && g.prec == prec && g.has_mask == has_mask && g.cfg == cfg_on &&
+                    g.scale == scale && g.plan.size() == (size_t)n_evals * PDM_PLAN_STRIDE &&
+                    std::memcmp(g.plan.data(), plan, g.plan.size() * sizeof(float)) == 0) {
+                    hit = &g;
+                    break;
+                }
+            }
+            if (!hit) {
+                cudaGraph_t graph = nullptr;
+                const long long count_before = g_launch_count.load();
+                PDM_CHECK_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+                try {
+                    enqueue_loop(ws, plan, n_evals, B, has_mask, cfg_on, scale, prec, s);
+                } catch (...) {
+                    cudaStreamEndCapture(s, &graph);
+                    if (graph) cudaGraphDestroy(graph);
+                    throw;
+                }
+                PDM_CHECK_CUDA(cudaStreamEndCapture(s, &graph));
+                GraphEntry e;
+                e.n_kernels = g_launch_count.load() - count_before;  // captured, not executed yet
+                g_launch_count.store(count_before);
+                cudaError_t ie = cudaGraphInstantiate(&e.exec, graph, 0);
+                cudaGraphDestroy(graph);
+                PDM_REQUIRE(ie == cudaSuccess, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ie));
+                e.plan.assign(plan, plan + (size_t)n_evals * PDM_PLAN_STRIDE);
+                e.scale = scale; e.B = B; e.prec = prec; e.has_mask = has_mask; e.cfg = cfg_on; e.ws = &ws;
+                if (graphs.size() >= 8) {
+                    cudaGraphExecDestroy(graphs.front().exec);
+                    graphs.erase(graphs.begin());
+                }
+                graphs.push_back(e);
+                hit = &graphs.back();
+            }
+            PDM_CHECK_CUDA(cudaGraphLaunch(hit->exec, s));
+            // kernels replayed by the graph do not pass through check_launch: account for them here
+            g_launch_count.fetch_add(hit->n_kernels, std::memory_order_relaxed);
+        }
+        PDM_CHECK_CUDA(cudaMemcpyAsync(out_z, ws.xbase, img, cudaMemcpyDeviceToDevice, s));
+        if (has_mask) PDM_CHECK_CUDA(cudaMemcpyAsync(out_pm, ws.P0, msk, cudaMemcpyDeviceToDevice, s));
+    }
+};
+
+// ---------------------------------------------------------------------------------------------- C ABI
+namespace {
+template <typename F>
+int guard(F&& f) {
+    try {
+        f();
+        return 0;
+    } catch (const std::exception& e) {
+        g_last_error = e.what();
+        return 1;
+    } catch (...) {
+        g_last_error = "unknown error";
+        return 1;
+    }
+}
+}  // namespace
+
+namespace pdm_dbg {
+struct DevBuf {
+    void* p = nullptr;
+    explicit DevBuf(size_t bytes) { PDM_CHECK_CUDA(cudaMalloc(&p, bytes ? bytes : 16)); }
+    ~DevBuf() { cudaFree(p); }
+};
+__global__ void bf16_to_f32_kernel(const bf16* in, float* out, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = __bfloat162float(in[i]);
+}
+template <typename F>
+void time_kernel(F&& launch, int iters, float* ms, cudaStream_t s) {
+    if (iters <= 0 || !ms) return;
+    cudaEvent_t a, b;
+    PDM_CHECK_CUDA(cudaEventCreate(&a));
+    PDM_CHECK_CUDA(cudaEventCreate(&b));
+    PDM_CHECK_CUDA(cudaEventRecord(a, s));
+    for (int i = 0; i < iters; ++i) launch();
+    PDM_CHECK_CUDA(cudaEventRecord(b, s));
+    PDM_CHECK_CUDA(cudaEventSynchronize(b));
+    float t = 0.f;
+    PDM_CHECK_CUDA(cudaEventElapsedTime(&t, a, b));
+    *ms = t / iters;
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+}
+}  // namespace pdm_dbg
+using namespace pdm_dbg;
+
+extern "C" {
+
+int pdm_create(const pdm_config* c, pdm_handle* out) {
+    return guard([&] {
+        PDM_REQUIRE(c && out, "null argument");
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        PDM_REQUIRE(e == cudaSuccess && ndev > 0, "no CUDA device: libpdm has no CPU path");
+        PDM_REQUIRE(c->embed_dim % 64 == 0 && c->num_heads * 64 == c->embed_dim, "head dim must be 64");
+        PDM_REQUIRE(c->depth % 2 == 0 && c->depth >= 2, "depth must be even");
+        PDM_REQUIRE(c->img_size % c->patch_size == 0, "img_size must be divisible by patch_size");
+        PDM_REQUIRE(c->clip_dim % 8 == 0, "clip_dim must be a multiple of 8");
+        PDM_REQUIRE(!c->separate || c->enable_panoptic, "separate=True requires enable_panoptic=True");
+        std::unique_ptr<pdm_engine> h(new pdm_engine());
+        h->cfg = *c;
+        h->D = c->embed_dim; h->H = c->num_heads; h->S = c->img_size; h->p = c->patch_size;
+        h->g = h->S / h->p; h->P = h->g * h->g; h->T = c->num_clip_token; h->ext = 1 + h->T;
+        h->C = c->in_chans; h->Cm = c->num_panoptic_class; h->depth = c->depth;
+        h->two = c->separate != 0;
+        h->L1 = h->ext + h->P;
+        h->L2 = h->ext + 2 * h->P;
+        h->declare_params();
+        // sinusoidal frequencies exactly as libs/uvit_t2i.py:30-33 builds them (float32 ops)
+        const int half = h->D / 2;
+        std::vector<float> f(half);
+        const float neg_log = -(float)9.210340371976184;  // -log(10000) rounded to float32
+        for (int i = 0; i < half; ++i) f[i] = expf(neg_log * (float)i / (float)half);
+        PDM_CHECK_CUDA(cudaMalloc(&h->freqs, half * sizeof(float)));
+        PDM_CHECK_CUDA(cudaMemcpy(h->freqs, f.data(), half * sizeof(float), cudaMemcpyHostToDevice));
+        *out = h.release();
+    });
+}
+
+int pdm_destroy(pdm_handle h) {
+    return guard([&] {
+        if (h) {
+            cudaDeviceSynchronize();
+            delete h;
+        }
+    });
+}
+
+int pdm_set_param(pdm_handle h, const char* key, const void* dev_f32, const int64_t* shape, int32_t ndim, void* stream) {
+    return guard([&] {
+        PDM_REQUIRE(h && key && dev_f32 && shape, "null argument");
+        h->set_param(key, dev_f32, shape, ndim, (cudaStream_t)stream);
+    });
+}
+
+int pdm_finalize_params(pdm_handle h, void* stream) {
+    return guard([&] {
+        PDM_REQUIRE(h, "null handle");
+        h->finalize((cudaStream_t)stream);
+    });
+}
+
+int pdm_workspace_bytes(pdm_handle h, int32_t n, int32_t precision, size_t* bytes) {
+    return guard([&] {
+        PDM_REQUIRE(h && bytes && n > 0, "bad argument");
+        *bytes = h->workspace_bytes(n, precision, h->cfg.enable_panoptic != 0);
+    });
+}
+
+int pdm_nnet_forward(pdm_handle h, const float* x, const float* t, const float* ctx, const float* mask, float* out_noise,
+                     float* out_mask, int32_t n, int32_t precision, void* stream) {
+    return guard([&] {
+        PDM_REQUIRE(h && x && t && ctx && out_noise && n > 0, "null argument");
+        PDM_REQUIRE(h->finalized, "parameters not finalized");
+        PDM_REQUIRE(precision == PDM_PREC_BF16 || precision == PDM_PREC_FP32, "bad precision");
+        PDM_REQUIRE(!mask || h->cfg.enable_panoptic, "model built with enable_panoptic=False cannot take a mask");
+        PDM_REQUIRE(!mask || out_mask, "out_mask required when mask is given");
+        cudaStream_t s = (cudaStream_t)stream;
+        Workspace& ws = h->workspace(n, precision, mask != nullptr);
+        PDM_CHECK_CUDA(cudaMemcpyAsync(ws.ctx_all, ctx, (size_t)n * h->T * h->cfg.clip_dim * 4, cudaMemcpyDeviceToDevice, s));
+        h->compute_ctxtok(ws, n, precision, s);
+        h->forward(ws, x, mask, n, n, t, 0.f, out_noise, out_mask, precision, s);
+    });
+}
+
+int pdm_cfg_update(const float* eps_c, const float* eps_u, const float* pm_c, const float* pm_u, const float* x_in,
+                   const float* x_base, float* X0, float* x_out, const float* m_base, float* P0, float* m_out,
+                   const float* coef, float cfg_scale, int64_t n_img, int64_t n_mask, void* stream) {
+    return guard([&] {
+        PDM_REQUIRE(eps_c && x_in && x_base && X0 && x_out && coef, "null argument");
+        UpdateArgs u;
+        u.eps_c = eps_c; u.eps_u = eps_u; u.pm_c = pm_c; u.pm_u = pm_u; u.x_in = x_in; u.x_base = x_base;
+        u.X0 = X0; u.x_out = x_out; u.m_base = m_base; u.P0 = P0; u.m_out = m_out;
+        u.alpha = coef[1]; u.sigma = coef[2]; u.A = coef[3]; u.B_img = coef[4]; u.C_img = coef[5];
+        u.B_msk = coef[6]; u.C_msk = coef[7]; u.scale = cfg_scale;
+        u.stage = (int)coef[8]; u.has_c = coef[9] != 0.f ? 1 : 0;
+        u.n_img = n_img; u.n_mask = pm_c ? n_mask : 0;
+        cfg_solver_update(u, (cudaStream_t)stream);
+    });
+}
+
+int pdm_sample(pdm_handle h, const float* plan, int32_t n_evals, const float* z_init, const float* mask_init,
+               const float* ctx, const float* empty_ctx, float cfg_scale, float* out_z, float* out_pred_mask, int32_t B,
+               int32_t precision, int32_t use_graph, void* stream) {
+    return guard([&] {
+        PDM_REQUIRE(h && plan && z_init && ctx && out_z, "null argument");
+        PDM_REQUIRE(precision == PDM_PREC_BF16 || precision == PDM_PREC_FP32, "bad precision");
+        h->sample(plan, n_evals, z_init, mask_init, ctx, empty_ctx, cfg_scale, out_z, out_pred_mask, B, precision,
+                  use_graph != 0, (cudaStream_t)stream);
+    });
+}
+
+int pdm_bits2int(const float* pred_mask, int32_t* labels, int32_t B, int32_t nbits, int32_t hw, void* stream) {
+    return guard([&] {
+        PDM_REQUIRE(pred_mask && labels, "null argument");
+        bits2int(pred_mask, labels, B, nbits, hw, (cudaStream_t)stream);
+    });
+}
+int pdm_int2bits(const int32_t* ids, float* bits, int32_t B, int32_t nbits, int32_t hw, void* stream) {
+    return guard([&] {
+        PDM_REQUIRE(ids && bits, "null argument");
+        int2bits(ids, bits, B, nbits, hw, (cudaStream_t)stream);
+    });
+}
+
+int pdm_debug_linear(const float* A, const float* A2, const float* W, const float* bias, const float* resid,
+                     float* out, int32_t M, int32_t N, int32_t K, int32_t K2, int32_t precision, int32_t gelu,
+                     int32_t iters, float* ms, void* stream) {
+    return guard([&] {
+        PDM_REQUIRE(A && W && out && M > 0 && N > 0 && K > 0, "bad argument");
+        cudaStream_t s = (cudaStream_t)stream;
+        const int Kt = K + (A2 ? K2 : 0);
+        GemmProblem g;
+        g.K1 = K; g.K2 = A2 ? K2 : 0; g.N = N; g.nb = 1; g.Lr = M; g.bias = bias; g.resid = resid; g.gelu = gelu != 0;
+        g.out32 = out;
+        if (precision == PDM_PREC_FP32) {
+            g.A1 = A; g.A2 = A2; g.W32 = W;
+            gemm_simt_f32(g, s);
+            time_kernel([&] { gemm_simt_f32(g, s); }, resid ? 0 : iters, ms, s);
+        } else {
+            DevBuf a16((size_t)M * K * 2), a216((size_t)M * (A2 ? K2 : 0) * 2), w16((size_t)N * Kt * 2);
+            convert_f32_bf16(A, (bf16*)a16.p, (long long)M * K, s);
+            if (A2) convert_f32_bf16(A2, (bf16*)a216.p, (long long)M * K2, s);
+            convert_f32_bf16(W, (bf16*)w16.p, (long long)N * Kt, s);
+            g.A1 = a16.p; g.A2 = A2 ? a216.p : nullptr; g.W16 = (const bf16*)w16.p;
+            gemm_tc_bf16(g, s);
+            // timing re-runs the identical launch; with a residual the output keeps accumulating, so
+            // callers time without `resid` aliasing `out` (resid given -> extra launches use out as scratch)
+            time_kernel([&] { gemm_tc_bf16(g, s); }, iters, ms, s);
+            PDM_CHECK_CUDA(cudaStreamSynchronize(s));
+        }
+    });
+}
+
+int pdm_debug_attention(const float* qkv, float* out, int32_t nb, int32_t L, int32_t H, int32_t precision,
+                        int32_t iters, float* ms, void* stream) {
+    return guard([&] {
+        PDM_REQUIRE(qkv && out && nb > 0 && L > 0 && H > 0, "bad argument");
+        cudaStream_t s = (cudaStream_t)stream;
+        const long long nq = (long long)nb * L * 3 * H * 64, no = (long long)nb * L * H * 64;
+        if (precision == PDM_PREC_FP32) {
+            attention_simt(qkv, out, nb, L, H, false, s);
+            time_kernel([&] { attention_simt(qkv, out, nb, L, H, false, s); }, iters, ms, s);
+        } else {
+            DevBuf q16(nq * 2), o16(no * 2);
+            convert_f32_bf16(qkv, (bf16*)q16.p, nq, s);
+            attention_tc_bf16((const bf16*)q16.p, (bf16*)o16.p, nb, L, H, s);
+            time_kernel([&] { attention_tc_bf16((const bf16*)q16.p, (bf16*)o16.p, nb, L, H, s); }, iters, ms, s);
+            bf16_to_f32_kernel<<<(unsigned)ceil_div_ll(no, 256), 256, 0, s>>>((const bf16*)o16.p, out, no);
+            check_launch("bf16_to_f32");
+            PDM_CHECK_CUDA(cudaStreamSynchronize(s));
+        }
+    });
+}
+
+int pdm_debug_layernorm(const float* x, const float* w, const float* b, float* out, int64_t rows, int32_t D,
+                        int32_t precision, int32_t iters, float* ms, void* stream) {
+    return guard([&] {
+        PDM_REQUIRE(x && w && b && out && rows > 0 && D > 0, "bad argument");
+        cudaStream_t s = (cudaStream_t)stream;
+        if (precision == PDM_PREC_FP32) {
+            layernorm(x, w, b, out, false, rows, D, s);
+            time_kernel([&] { layernorm(x, w, b, out, false, rows, D, s); }, iters, ms, s);
+        } else {
+            DevBuf o16((size_t)rows * D * 2);
+            layernorm(x, w, b, o16.p, true, rows, D, s);
+            time_kernel([&] { layernorm(x, w, b, o16.p, true, rows, D, s); }, iters, ms, s);
+            bf16_to_f32_kernel<<<(unsigned)ceil_div_ll(rows * D, 256), 256, 0, s>>>((const bf16*)o16.p, out, rows * D);
+            check_launch("bf16_to_f32");
+            PDM_CHECK_CUDA(cudaStreamSynchronize(s));
+        }
+    });
+}
+
+const char* pdm_last_error(void) { return g_last_error.c_str(); }
+int pdm_abi_version(void) { return PDM_ABI_VERSION; }
+int64_t pdm_launch_count(void) { return (int64_t)g_launch_count.load(); }
+
+int pdm_set_profiling(pdm_handle h, int32_t enabled) {
+    return guard([&] {
+        PDM_REQUIRE(h, "null handle");
+        h->profiling = enabled != 0;
+        for (auto& e : h->prof) {
+            cudaEventDestroy(e.a);
+            cudaEventDestroy(e.b);
+        }
+        h->prof.clear();
+    });
+}
+
+int pdm_get_profile(pdm_handle h, float* ms, int32_t cap, char* name_buf, int32_t name_cap, int32_t* count) {
+    return guard([&] {
+        PDM_REQUIRE(h && ms && name_buf && count, "null argument");
+        PDM_CHECK_CUDA(cudaDeviceSynchronize());
+        std::vector<std::string> names;
+        std::vector<float> tot;
+        std::vector<int> cnt;
+        for (auto& e : h->prof) {
+            float t = 0.f;
+            if (cudaEventElapsedTime(&t, e.a, e.b) != cudaSuccess) continue;
+            size_t i = 0;
+            for (; i < names.size(); ++i)
+                if (names[i] == e.name) break;
+            if (i == names.size()) {
+                names.push_back(e.name);
+                tot.push_back(0.f);
+                cnt.push_back(0);
+            }
+            tot[i] += t;
+            cnt[i] += 1;
+        }
+        std::string joined;
+        int n = 0;
+        for (size_t i = 0; i < names.size() && n < cap; ++i, ++n) {
+            ms[n] = tot[i];
+            joined += names[i] + ":" + std::to_string(cnt[i]) + "\n";
+        }
+        PDM_REQUIRE((int)joined.size() + 1 <= name_cap, "name buffer too small");
+        std::memcpy(name_buf, joined.c_str(), joined.size() + 1);
+        *count = n;
+        for (auto& e : h->prof) {
+            cudaEventDestroy(e.a);
+            cudaEventDestroy(e.b);
+        }
+        h->prof.clear();
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,100 @@
+"""Host planner (panopticdiffusionmodels_b200.dpm_solver_pp.build_plan) against the oracle: the plan,
+executed by a plain-torch emulation of the K12 kernel arithmetic, must reproduce the oracle's joint
+sample bit for bit (the oracle itself is pinned to the reference in test_oracle_golden.py)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import TINY, load_golden
+from oracle import dpm_oracle
+from panopticdiffusionmodels_b200 import dpm_solver_pp as P
+
+
+def emulate_plan(plan, model, x, m):
+    """Same dataflow as pdm_sample / update_kernel (csrc/elementwise.cu), CFG already inside `model`."""
+    f = torch.float32
+    xbase, mbase = x.clone(), (None if m is None else m.clone())
+    xin = X0 = min_ = P0 = None
+    for rec in plan:
+        rec = [torch.tensor(float(v), dtype=f) for v in rec]
+        stage, has_c, last = int(rec[8]), rec[9] != 0, rec[10] != 0
+        cur_x = xbase if stage == 0 else xin
+        cur_m = mbase if (stage == 0 or m is None) else min_
+        eps, pm = model(cur_x, rec[0] / 1000.0, cur_m)
+        X = (cur_x - rec[2] * eps) / rec[1]
+        if stage == 0:
+            X0, P0 = X, pm
+        out = rec[3] * xbase + rec[4] * X0
+        if has_c:
+            out = out + rec[5] * (X - X0)
+        if m is not None:
+            mo = rec[3] * mbase + rec[6] * P0
+            if has_c:
+                mo = mo + rec[7] * (pm - P0)
+        if last:
+            xbase = out
+            if m is not None:
+                mbase = mo
+        else:
+            xin = out
+            if m is not None:
+                min_ = mo
+    return xbase, P0
+
+
+def test_schedule_matches_oracle():
+    ns = P.NoiseScheduleVP("discrete", betas=dpm_oracle.sd_betas())
+    s = dpm_oracle.Schedule()
+    ts = torch.linspace(1.0, 1e-3, 51)
+    for t in ts:
+        assert float(ns.marginal_lambda(t)) == float(s.lam(t))
+        assert float(ns.marginal_std(t)) == float(s.sigma(t))
+        assert float(ns.inverse_lambda(s.lam(t))) == float(s.inv_lam(s.lam(t)))
+    g, _ = load_golden("schedule.npz")
+    assert torch.equal(ns.marginal_log_mean_coeff(g["t"]), g["log_alpha"])
+    assert torch.equal(ns.inverse_lambda(g["lam"]), g["inv_lam"])
+
+
+def test_orders():
+    for steps in range(3, 60):
+        assert P.fast_orders(steps, 3) == dpm_oracle.fast_orders(steps, 3)
+        assert sum(P.fast_orders(steps, 3)) == steps
+    assert P.fast_orders(50, 3) == [3] * 16 + [2]
+    assert P.fast_orders(20, 3) == [3] * 6 + [2]
+    assert P.fast_orders(5, 2) == [2, 2, 1]
+
+
+def test_plan_shape_and_times():
+    ns = P.NoiseScheduleVP("discrete", betas=dpm_oracle.sd_betas())
+    plan = P.build_plan(ns, 50, 3, eps=1e-3, T=1.0)
+    assert plan.shape == (50, P.PLAN_STRIDE) and plan.dtype == np.float32
+    assert plan[0, 0] == 1000.0 and abs(plan[1, 0] - 980.02) < 1e-2 and abs(plan[-1, 0] - 20.98) < 2e-2
+    assert list(plan[:6, 8]) == [0, 1, 2, 0, 1, 2] and list(plan[-2:, 8]) == [0, 1]
+    assert list(plan[:3, 10]) == [0, 0, 1] and plan[-1, 10] == 1
+    # sign quirk: at stage 0 the mask coefficient has the opposite sign of the image one
+    assert plan[0, 4] == -plan[0, 6] and plan[0, 6] < 0
+    assert plan[1, 4] == plan[1, 6] and plan[2, 5] == plan[2, 7]
+
+
+@pytest.mark.parametrize("name,separate", [("single", False), ("two", True)])
+@pytest.mark.parametrize("steps", [20, 7, 9])
+def test_plan_reproduces_oracle_bit_exact(name, separate, steps):
+    g, sd = load_golden(f"tiny_{name}.npz")
+    cfg = dict(TINY, separate=separate)
+    model = dpm_oracle.cfg_model(sd, cfg, g["ctx"], g["empty"], float(g["scale"]))
+    z_ref, pm_ref = dpm_oracle.Solver(model, dpm_oracle.Schedule()).sample_fast(g["x"], g["m"], steps)
+    ns = P.NoiseScheduleVP("discrete", betas=dpm_oracle.sd_betas())
+    plan = P.build_plan(ns, steps, 3, eps=1e-3, T=1.0)
+    assert plan.shape[0] == steps
+    z, pm = emulate_plan(plan, model, g["x"], g["m"])
+    assert torch.equal(z, z_ref)
+    assert torch.equal(pm, pm_ref)
+
+
+def test_plan_image_only():
+    g, sd = load_golden("tiny_single.npz")
+    model = dpm_oracle.cfg_model(sd, dict(TINY, separate=False), g["ctx"], g["empty"], 2.0)
+    z_ref, _ = dpm_oracle.Solver(model, dpm_oracle.Schedule()).sample_fast(g["x"], None, 8)
+    ns = P.NoiseScheduleVP("discrete", betas=dpm_oracle.sd_betas())
+    z, _ = emulate_plan(P.build_plan(ns, 8, 3, eps=1e-3, T=1.0), model, g["x"], None)
+    assert torch.equal(z, z_ref)
