@@ -114,8 +114,11 @@ struct pdm_engine {
     std::vector<GraphEntry> graphs;
     bool profiling = false;
     std::vector<ProfEvent> prof;
+    cudaStream_t cap_stream = nullptr;  // private stream used only to CAPTURE graphs (the legacy default
+                                        // stream, which torch uses by default, cannot be captured)
 
     ~pdm_engine() {
+        if (cap_stream) cudaStreamDestroy(cap_stream);
         for (auto& kv : params) {
             if (kv.second.d32) cudaFree(kv.second.d32);
             if (kv.second.d16) cudaFree(kv.second.d16);
@@ -615,15 +618,16 @@ struct pdm_engine {
             if (!hit) {
                 cudaGraph_t graph = nullptr;
                 const long long count_before = g_launch_count.load();
-                PDM_CHECK_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+                if (!cap_stream) PDM_CHECK_CUDA(cudaStreamCreateWithFlags(&cap_stream, cudaStreamNonBlocking));
+                PDM_CHECK_CUDA(cudaStreamBeginCapture(cap_stream, cudaStreamCaptureModeThreadLocal));
                 try {
-                    enqueue_loop(ws, plan, n_evals, B, has_mask, cfg_on, scale, prec, s);
+                    enqueue_loop(ws, plan, n_evals, B, has_mask, cfg_on, scale, prec, cap_stream);
                 } catch (...) {
-                    cudaStreamEndCapture(s, &graph);
+                    cudaStreamEndCapture(cap_stream, &graph);
                     if (graph) cudaGraphDestroy(graph);
                     throw;
                 }
-                PDM_CHECK_CUDA(cudaStreamEndCapture(s, &graph));
+                PDM_CHECK_CUDA(cudaStreamEndCapture(cap_stream, &graph));
                 GraphEntry e;
                 e.n_kernels = g_launch_count.load() - count_before;  // captured, not executed yet
                 g_launch_count.store(count_before);
