@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""bench.py -- joint image+mask samples/sec (DPM-Solver++ 50 NFE, CFG) on N B200s.
+
+A "step" is one full pass of the hot path over one synthetic batch: a complete 50-NFE classifier-free-
+guided joint sample of `--batch` images+masks per GPU (= 100 U-ViT forwards on 2B rows + 50 fused
+CFG/solver updates), VAE / CLIP excluded (they run once per sample outside the loop).
+
+  python bench.py --gpus 1 --steps 3 --warmup 3                  # our arm (libpdm, bf16)
+  python bench.py --impl reference --steps 1 --warmup 1          # CPU arm: oracle port on the host cores
+  torchrun --nproc-per-node N bench.py --gpus N ...              # weak scaling: batch per GPU fixed
+
+One JSON line on stdout (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "joint image+mask samples/sec (DPM-Solver++ 50 steps)"
+CONFIG_NAMES = {"small": "mscoco_uvit_small", "mid": "mscoco_uvit_mid", "large": "mscoco_uvit_large",
+                "small_512": "mscoco_uvit_small_512"}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="small", choices=list(CONFIG_NAMES))
+    ap.add_argument("--batch", type=int, default=0, help="samples per GPU per step (default: BASELINE config)")
+    ap.add_argument("--nfe", type=int, default=50)
+    ap.add_argument("--scale", type=float, default=2.0)
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--single-stream", action="store_true", help="override separate=True of the shipped small config")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-kernel-profile", action="store_true")
+    return ap.parse_args()
+
+
+def default_batch(config: str, gpus: int) -> int:
+    # BASELINE.json configs: small 256/GPU; mid 512 global; large 1024 global over 8; small_512 256 global over 8
+    return {"small": 256, "mid": max(64, 512 // max(gpus, 2)), "large": 128, "small_512": 32}[config]
+
+
+def nnet_kwargs(a):
+    from panopticdiffusionmodels_b200 import configs
+    cfg = configs.get_config(CONFIG_NAMES[a.config])
+    kw = dict(cfg.nnet)
+    kw.pop("name")
+    if a.config == "mid":
+        kw["enable_panoptic"] = True  # BASELINE config 3 is the joint model
+    if a.single_stream:
+        kw["separate"] = False
+    return cfg, kw
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        self.stop_flag.set()
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(sm), "power_w_max": max(float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit())}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_eval_rate(kw, nfe, scale, steps=1, warmup=1, batch=2):
+    """Oracle port (oracle/*.py = CPU restatement of the reference path) on the host cores.
+    Bounded sample: `steps` CFG model evaluations (2 forwards each) at batch `batch`; a full sample costs
+    `nfe` such evaluations, so samples/s = batch / (nfe * t_eval)."""
+    import torch
+    from oracle import dpm_oracle
+    from panopticdiffusionmodels_b200.libs.uvit_t2i import UViT
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(1234)
+    net = UViT(**kw)
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    S = kw["img_size"]
+    g = torch.Generator().manual_seed(1234)
+    x, m = torch.randn(batch, 4, S, S, generator=g), torch.randn(batch, 8, S, S, generator=g)
+    ctx, empty = torch.randn(batch, 77, 768, generator=g), torch.randn(77, 768, generator=g)
+    model = dpm_oracle.cfg_model(sd, kw, ctx, empty, scale)
+    t = torch.tensor(0.5)
+    with torch.no_grad():
+        for _ in range(warmup):
+            model(x, t, m)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            model(x, t, m)
+        dt = (time.perf_counter() - t0) / steps
+    return dict(value=batch / (nfe * dt), unit="samples/s", cores=torch.get_num_threads(), kind="port",
+                sample=f"{steps} CFG model evaluation(s) (2 U-ViT forwards each) at batch {batch}, fp32, extrapolated x{nfe} evals/sample",
+                s_per_eval=dt)
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg, kw = nnet_kwargs(a)
+    B = a.batch or default_batch(a.config, a.gpus)
+    cb = cpu_eval_rate(kw, a.nfe, a.scale, steps=max(1, a.steps), warmup=max(1, min(a.warmup, 1)))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "samples/s", "n_gpus": a.gpus,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": cb["s_per_eval"] * a.nfe * 1e3 * (B / 2),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload(a, kw, B), "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": cb["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload(a, kw, B):
+    topo = "two-stream (separate=True, as shipped)" if kw.get("separate") else "single-stream"
+    return {"workload": f"{CONFIG_NAMES[a.config]} {topo} U-ViT D={kw['embed_dim']} depth={kw['depth']}, "
+                        f"{kw['img_size']}x{kw['img_size']}x4 latent + 8-bit mask, batch {B}/GPU, DPM-Solver++ fast order 3, "
+                        f"{a.nfe} NFE, CFG scale {a.scale}", "batch_per_gpu": B, "nfe": a.nfe, "cfg_scale": a.scale,
+            "precision": a.precision, "l2": "working set (GBs of activations) larger than L2; no flush needed",
+            "weights": "random-init (reference init, seed 1234; zero-conv bridges randomised)"}
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    from oracle import uvit_oracle  # flops formula only (bench bookkeeping; not on the measured path)
+    from panopticdiffusionmodels_b200 import _lib
+    from panopticdiffusionmodels_b200.libs.uvit_t2i import UViT
+    from panopticdiffusionmodels_b200.sampling import JointSampler
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg, kw = nnet_kwargs(a)
+    B = a.batch or default_batch(a.config, a.gpus)
+    S = kw["img_size"]
+
+    torch.manual_seed(1234)
+    net = UViT(**kw)
+    with torch.no_grad():
+        for k, p in net.named_parameters():
+            if k.startswith("zero_convs"):
+                torch.nn.init.trunc_normal_(p, std=0.02)
+    net = net.to(dev).eval()
+    net.precision = a.precision
+    js = JointSampler(net, z_shape=(4, S, S), mask_channels=8, scale=a.scale, cfg=True, sample_steps=a.nfe)
+
+    g = torch.Generator().manual_seed(1234 + rank)
+    pin = lambda *s: torch.randn(*s, generator=g).pin_memory()  # noqa: E731
+    h_ctx, h_empty, h_z, h_m = pin(B, 77, 768), pin(77, 768), pin(B, 4, S, S), pin(B, 8, S, S)
+    d_ctx, d_empty, d_z, d_m = (t.to(dev) for t in (h_ctx, h_empty, h_z, h_m))
+    out_host_z = torch.empty(B, 4, S, S).pin_memory()
+    out_host_m = torch.empty(B, 8, S, S).pin_memory()
+
+    def step_resident():
+        z, pm = js.sample(d_ctx, d_empty, z_init=d_z, mask_init=d_m)
+        if world > 1:  # the path's one exchange: all-gather of finished latents + mask predictions
+            gz = torch.empty(world * B, 4, S, S, device=dev)
+            gm = torch.empty(world * B, 8, S, S, device=dev)
+            dist.all_gather_into_tensor(gz, z)
+            dist.all_gather_into_tensor(gm, pm)
+            return gz, gm
+        return z, pm
+
+    def step_e2e():
+        c, e = h_ctx.to(dev, non_blocking=True), h_empty.to(dev, non_blocking=True)
+        z0, m0 = h_z.to(dev, non_blocking=True), h_m.to(dev, non_blocking=True)
+        z, pm = js.sample(c, e, z_init=z0, mask_init=m0)
+        out_host_z.copy_(z, non_blocking=True)
+        out_host_m.copy_(pm, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def timed(fn, steps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = _lib.launch_count()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), _lib.launch_count() - l0
+
+    for _ in range(max(a.warmup, 3)):
+        step_resident()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms, launches = timed(step_resident, a.steps)
+    clocks = sampler.summary() if sampler else None
+    step_e2e()
+    ms_e2e, _ = timed(step_e2e, a.steps)
+
+    samples = world * B * a.steps
+    value = samples / (ms / 1e3)
+    F = uvit_oracle.flops_per_forward(dict(kw, clip_dim=768), with_mask=True)   # per sample per forward
+    flops_step = 2 * a.nfe * F * B                                               # per GPU per step (cond + uncond)
+    pk = peaks()
+
+    # ---- per-kernel timing of one extra eager step with CUDA events around every launch (rank 0) ----
+    kern, roof = None, None
+    if rank == 0 and not a.no_kernel_profile:
+        import ctypes as C
+        L = _lib.lib()
+        h = net.engine()
+        _lib.check(L.pdm_set_profiling(h, 1))
+        js.sample(d_ctx, d_empty, z_init=d_z, mask_init=d_m)
+        buf_ms = (C.c_float * 64)()
+        names = C.create_string_buffer(4096)
+        cnt = C.c_int32(0)
+        _lib.check(L.pdm_get_profile(h, buf_ms, 64, names, 4096, C.byref(cnt)))
+        _lib.check(L.pdm_set_profiling(h, 0))
+        kern = {}
+        for i, nm in enumerate(names.value.decode().strip().split("\n")[:cnt.value]):
+            n, c = nm.rsplit(":", 1)
+            kern[n] = {"launches": int(c), "total_ms": round(buf_ms[i], 3), "avg_ms": round(buf_ms[i] / int(c), 4)}
+        tot = sum(v["total_ms"] for v in kern.values())
+        for v in kern.values():
+            v["share"] = round(v["total_ms"] / tot, 4)
+        gem = {k: v for k, v in kern.items() if k.startswith("gemm_")}
+        D, depth, P = kw["embed_dim"], kw["depth"], (S // 2) ** 2
+        two = bool(kw.get("separate"))
+        Ls = [78 + P, 78 + 2 * P] if two else [78 + 2 * P]
+        gemm_flops = sum((depth + 1) * 24 * Lx * D * D + (depth // 2) * 4 * Lx * D * D for Lx in Ls)
+        if two:
+            gemm_flops += (depth + 1) * 2 * (78 + P) * D * D
+        gemm_flops *= 2 * B * a.nfe                                            # whole step, this GPU
+        g_ms = sum(v["total_ms"] for v in gem.values())
+        g_n = sum(v["launches"] for v in gem.values())
+        ach = gemm_flops / (g_ms / 1e3) / 1e12
+        roof = {"kernel": "gemm_tc_kernel (tcgen05 bf16 GEMM: qkv/proj/fc1/fc2/skip/zero-conv)", "bound": "tensor",
+                "achieved": round(ach, 1), "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": round(ach / pk["tf_sust"], 4),
+                "peak_src": pk["src"] + " (sustained bf16)", "launches": g_n, "avg_launch_ms": round(g_ms / g_n, 4),
+                "flops_per_launch": gemm_flops / g_n, "share_of_step": round(g_ms / tot, 4), "traffic": None}
+
+    if rank == 0:
+        cb = None if a.no_cpu_baseline else cpu_eval_rate(kw, a.nfe, a.scale, steps=1, warmup=1)
+        h2d = (h_ctx.numel() + h_empty.numel() + h_z.numel() + h_m.numel()) * 4
+        d2h = (out_host_z.numel() + out_host_m.numel()) * 4
+        line = {
+            "metric": METRIC, "value": round(value, 3), "unit": "samples/s", "n_gpus": world, "steps": a.steps,
+            "warmup": max(a.warmup, 3), "ms_per_step": round(ms / a.steps, 2), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": a.precision, "data": "synthetic",
+            "config": workload(a, kw, B),
+            "ms_per_nnet_step": round(ms / a.steps / (2 * a.nfe), 3),
+            "ms_per_cfg_eval": round(ms / a.steps / a.nfe, 3),
+            "model_tflops_per_gpu": round(flops_step / (ms / a.steps / 1e3) / 1e12, 1),
+            "frac_of_bf16_peak": round(flops_step / (ms / a.steps / 1e3) / 1e12 / pk["tf_sust"], 4),
+            "e2e": {"value": round(samples / (ms_e2e / 1e3), 3), "unit": "samples/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "kernels": kern,
+            "cpu_baseline": None if cb is None else {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

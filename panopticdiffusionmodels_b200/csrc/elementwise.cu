@@ -141,65 +141,109 @@ void copy_rows(void* dst, int dst_bs, const void* src, int src_bs, int Lr, int n
 // Token embed (libs/uvit_t2i.py:382-406): time token | context tokens | image patches | mask patches,
 // + positional embedding, written straight into the residual stream(s).  One block per (token, row).
 // ----------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) embed_kernel(EmbedArgs a) {
-    const int tok = blockIdx.x;  // 0 .. ext + P + (mask ? P : 0)
+// Kernel A: time + context tokens (pure copy + positional add), float4 per thread.
+__global__ void __launch_bounds__(128) embed_extras_kernel(EmbedArgs a) {
+    const int tok = blockIdx.x;  // 0 .. T
     const int b = blockIdx.y;
-    const int ext = 1 + a.T;
-    const int g = a.S / a.p;
-    const int P = g * g;
     const int bi = b % a.Bx;
-    __shared__ float patch[64];
+    float* o = a.out_x + ((long long)b * a.Lx + tok) * a.D;
+    const float* pe = a.pos + (long long)tok * a.D;
     if (tok == 0) {
         const float t = a.t_dev ? a.t_dev[bi] : a.t_scalar;
         const int half = a.D / 2;
-        float* o = a.out_x + ((long long)b * a.Lx) * a.D;
         for (int d = threadIdx.x; d < a.D; d += blockDim.x) {
             float v = 0.f;
             if (d < 2 * half) {
                 const float arg = t * a.freqs[d < half ? d : d - half];
                 v = d < half ? cosf(arg) : sinf(arg);
             }
-            o[d] = v + a.pos[d];
+            o[d] = v + pe[d];
         }
-    } else if (tok < ext) {
-        const float* src = a.ctxtok + ((long long)b * a.T + (tok - 1)) * a.D;
-        const float* pe = a.pos + (long long)tok * a.D;
-        float* o = a.out_x + ((long long)b * a.Lx + tok) * a.D;
-        for (int d = threadIdx.x; d < a.D; d += blockDim.x) o[d] = src[d] + pe[d];
     } else {
-        const bool is_mask = tok >= ext + P;
-        const int pidx = is_mask ? tok - ext - P : tok - ext;
-        const int ph = pidx / g, pw = pidx % g;
-        const int C = is_mask ? a.Cm : a.C;
-        const float* src = (is_mask ? a.mask : a.img) + (long long)bi * C * a.S * a.S;
-        const int kk = C * a.p * a.p;  // <= 64
-        if (threadIdx.x < kk) {
-            const int c = threadIdx.x / (a.p * a.p), r = threadIdx.x % (a.p * a.p);
-            const int i = r / a.p, j = r % a.p;
-            patch[threadIdx.x] = src[((long long)c * a.S + (ph * a.p + i)) * a.S + (pw * a.p + j)];
+        const float4* src = reinterpret_cast<const float4*>(a.ctxtok + ((long long)b * a.T + (tok - 1)) * a.D);
+        const float4* p4 = reinterpret_cast<const float4*>(pe);
+        float4* o4 = reinterpret_cast<float4*>(o);
+        for (int d = threadIdx.x; d < a.D / 4; d += blockDim.x) {
+            const float4 u = __ldg(src + d), q = __ldg(p4 + d);
+            o4[d] = make_float4(u.x + q.x, u.y + q.y, u.z + q.z, u.w + q.w);
         }
-        __syncthreads();
-        const float* w = is_mask ? a.w_msk : a.w_img;
-        const float* bias = is_mask ? a.b_msk : a.b_img;
-        const float* pe = is_mask ? a.pos_m + (long long)pidx * a.D : a.pos + (long long)tok * a.D;
-        float* o = is_mask ? a.out_m + ((long long)b * a.Lm + a.m_off + pidx) * a.D
-                           : a.out_x + ((long long)b * a.Lx + tok) * a.D;
-        for (int d = threadIdx.x; d < a.D; d += blockDim.x) {
-            const float* wr = w + (long long)d * kk;
+    }
+}
+
+// Kernel B: patch embedding (Conv2d k = s = p == per-patch dot product, weight (D, C, p, p)) for the image and
+// the mask stream.  One block = 32 patches of one stream of one row; each thread owns output channels
+// d = tid, tid + 256, ... with its weight row in registers; patch pixels are broadcast from shared memory.
+// HBM-bound on the [tokens, D] fp32 write.
+constexpr int EMB_TOK = 32;
+template <int KK>
+__global__ void __launch_bounds__(256) embed_patch_kernel(EmbedArgs a) {
+    __shared__ __align__(16) float patch[EMB_TOK][KK];
+    const int g = a.S / a.p;
+    const int P = g * g;
+    const int ext = 1 + a.T;
+    const int tile = blockIdx.x, is_mask = blockIdx.y, b = blockIdx.z;
+    const int bi = b % a.Bx;
+    const int C = is_mask ? a.Cm : a.C;
+    const int pp = a.p * a.p;
+    const float* src = (is_mask ? a.mask : a.img) + (long long)bi * C * a.S * a.S;
+    for (int i = threadIdx.x; i < EMB_TOK * KK; i += blockDim.x) {
+        const int t = i / KK, k = i % KK;
+        const int pidx = tile * EMB_TOK + t;
+        float v = 0.f;
+        if (pidx < P && k < C * pp) {
+            const int ph = pidx / g, pw = pidx % g;
+            const int c = k / pp, r = k % pp;
+            v = src[((long long)c * a.S + ph * a.p + r / a.p) * a.S + pw * a.p + r % a.p];
+        }
+        patch[t][k] = v;
+    }
+    __syncthreads();
+    const float* w = is_mask ? a.w_msk : a.w_img;
+    const float* bias = is_mask ? a.b_msk : a.b_img;
+    const int kk = C * pp;
+    for (int d = threadIdx.x; d < a.D; d += blockDim.x) {
+        float wr[KK];
+#pragma unroll
+        for (int k = 0; k < KK; ++k) wr[k] = k < kk ? __ldg(w + (long long)d * kk + k) : 0.f;
+        const float bd = bias[d];
+        for (int t = 0; t < EMB_TOK; ++t) {
+            const int pidx = tile * EMB_TOK + t;
+            if (pidx >= P) break;
             float acc = 0.f;
-            for (int k = 0; k < kk; ++k) acc = fmaf(wr[k], patch[k], acc);
-            o[d] = acc + bias[d] + pe[d];
+#pragma unroll
+            for (int k = 0; k < KK; k += 4) {
+                const float4 pv = *reinterpret_cast<const float4*>(&patch[t][k]);
+                acc = fmaf(wr[k], pv.x, acc);
+                acc = fmaf(wr[k + 1], pv.y, acc);
+                acc = fmaf(wr[k + 2], pv.z, acc);
+                acc = fmaf(wr[k + 3], pv.w, acc);
+            }
+            if (is_mask) {
+                a.out_m[((long long)b * a.Lm + a.m_off + pidx) * a.D + d] = acc + bd + a.pos_m[(long long)pidx * a.D + d];
+            } else {
+                const int tok = ext + pidx;
+                a.out_x[((long long)b * a.Lx + tok) * a.D + d] = acc + bd + a.pos[(long long)tok * a.D + d];
+            }
         }
     }
 }
 
 void embed_tokens(const EmbedArgs& a, cudaStream_t s) {
-    PDM_REQUIRE(a.C * a.p * a.p <= 64 && a.Cm * a.p * a.p <= 64, "embed: patch dimension > 64 unsupported");
+    const int kmax = std::max(a.C, a.mask ? a.Cm : 0) * a.p * a.p;
+    PDM_REQUIRE(kmax <= 64, "embed: patch dimension > 64 unsupported");
+    PDM_REQUIRE(a.D % 4 == 0, "embed: D must be a multiple of 4");
     const int g = a.S / a.p;
-    const int ntok = 1 + a.T + g * g + (a.mask ? g * g : 0);
-    dim3 grid(ntok, a.nb);
-    embed_kernel<<<grid, 256, 0, s>>>(a);
-    check_launch("embed");
+    const int P = g * g;
+    embed_extras_kernel<<<dim3(1 + a.T, a.nb), 128, 0, s>>>(a);
+    check_launch("embed_extras");
+    dim3 grid(ceil_div(P, EMB_TOK), a.mask ? 2 : 1, a.nb);
+    if (kmax <= 16)
+        embed_patch_kernel<16><<<grid, 256, 0, s>>>(a);
+    else if (kmax <= 32)
+        embed_patch_kernel<32><<<grid, 256, 0, s>>>(a);
+    else
+        embed_patch_kernel<64><<<grid, 256, 0, s>>>(a);
+    check_launch("embed_patch");
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -207,6 +251,7 @@ void embed_tokens(const EmbedArgs& a, cudaStream_t s) {
 // unpatchify -> 3x3 conv (+ tanh on the mask).
 // Kernel 1: one warp per (row, patch, stream); kernel 2: one thread per output pixel.
 // ----------------------------------------------------------------------------------------------
+template <int NV>
 __global__ void __launch_bounds__(256) head_token_kernel(HeadArgs a) {
     const int g = a.S / a.p;
     const int P = g * g;
@@ -221,20 +266,43 @@ __global__ void __launch_bounds__(256) head_token_kernel(HeadArgs a) {
                                    : a.m + ((long long)b * a.Lm + a.m_off + pidx) * a.D;
     const bool do_ln = stream == 0 || a.ln_m;
     const int D = a.D;
-    // pass 1: mean / rstd
-    float mean = 0.f, rstd = 1.f;
+    // the (optionally normalised) token row lives in registers: lane owns float4 chunks lane + 32 i
+    float4 v[NV];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = lane + 32 * i;
+        v[i] = c * 4 < D ? __ldg(reinterpret_cast<const float4*>(row) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
     if (do_ln) {
-        float sum = 0.f;
-        for (int d = lane; d < D; d += 32) sum += row[d];
+#pragma unroll
         for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        mean = sum / (float)D;
+        const float mean = sum / (float)D;
         float sq = 0.f;
-        for (int d = lane; d < D; d += 32) {
-            const float t = row[d] - mean;
-            sq += t * t;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = lane + 32 * i;
+            if (c * 4 < D) {
+                const float e0 = v[i].x - mean, e1 = v[i].y - mean, e2 = v[i].z - mean, e3 = v[i].w - mean;
+                sq += (e0 * e0 + e1 * e1) + (e2 * e2 + e3 * e3);
+            }
         }
+#pragma unroll
         for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-        rstd = rsqrtf(sq / (float)D + 1e-5f);
+        const float rstd = rsqrtf(sq / (float)D + 1e-5f);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = lane + 32 * i;
+            if (c * 4 < D) {
+                const float4 w4 = __ldg(reinterpret_cast<const float4*>(a.ln_w) + c);
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.ln_b) + c);
+                v[i].x = (v[i].x - mean) * rstd * w4.x + b4.x;
+                v[i].y = (v[i].y - mean) * rstd * w4.y + b4.y;
+                v[i].z = (v[i].z - mean) * rstd * w4.z + b4.z;
+                v[i].w = (v[i].w - mean) * rstd * w4.w + b4.w;
+            }
+        }
     }
     const int C = stream == 0 ? a.C : a.Cm;
     const int nout = a.p * a.p * C;
@@ -242,20 +310,32 @@ __global__ void __launch_bounds__(256) head_token_kernel(HeadArgs a) {
     const float* bias = stream == 0 ? a.b_dec : a.b_decm;
     float* dst = (stream == 0 ? a.tmp_img : a.tmp_msk) + (long long)b * C * a.S * a.S;
     const int ph = pidx / g, pw = pidx % g;
+    float mine = 0.f;  // lane o keeps output o
     for (int o = 0; o < nout; ++o) {
-        const float* wr = W + (long long)o * D;
+        const float4* wr = reinterpret_cast<const float4*>(W + (long long)o * D);
         float acc = 0.f;
-        for (int d = lane; d < D; d += 32) {
-            float v = row[d];
-            if (do_ln) v = (v - mean) * rstd * a.ln_w[d] + a.ln_b[d];
-            acc = fmaf(v, wr[d], acc);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = lane + 32 * i;
+            if (c * 4 < D) {
+                const float4 w4 = __ldg(wr + c);
+                acc = fmaf(v[i].x, w4.x, acc);
+                acc = fmaf(v[i].y, w4.y, acc);
+                acc = fmaf(v[i].z, w4.z, acc);
+                acc = fmaf(v[i].w, w4.w, acc);
+            }
         }
+#pragma unroll
         for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-        if (lane == 0) {
-            // feature o = (p1 * p + p2) * C + c  ->  pixel (ph*p + p1, pw*p + p2), channel c
-            const int c = o % C, pp = o / C;
-            const int p1 = pp / a.p, p2 = pp % a.p;
-            dst[((long long)c * a.S + ph * a.p + p1) * a.S + pw * a.p + p2] = acc + bias[o];
+        if ((o & 31) == lane) mine = acc;
+        if ((o & 31) == 31 || o == nout - 1) {
+            const int oo = (o & ~31) + lane;
+            if (oo <= o) {
+                // feature oo = (p1 * p + p2) * C + c  ->  pixel (ph*p + p1, pw*p + p2), channel c
+                const int c = oo % C, pq = oo / C;
+                const int p1 = pq / a.p, p2 = pq % a.p;
+                dst[((long long)c * a.S + ph * a.p + p1) * a.S + pw * a.p + p2] = mine + bias[oo];
+            }
         }
     }
 }
@@ -293,7 +373,15 @@ void head_decode(const HeadArgs& a, cudaStream_t s) {
     const int g = a.S / a.p;
     const int P = g * g;
     const int nwarps = a.nb * P * (a.m ? 2 : 1);
-    head_token_kernel<<<ceil_div(nwarps, 8), 256, 0, s>>>(a);
+    PDM_REQUIRE(a.D % 4 == 0 && a.D <= 2048, "head: D must be a multiple of 4 and <= 2048");
+    const int nv = ceil_div(a.D, 128);
+    const int hgrid = ceil_div(nwarps, 8);
+    if (nv <= 1) head_token_kernel<1><<<hgrid, 256, 0, s>>>(a);
+    else if (nv <= 2) head_token_kernel<2><<<hgrid, 256, 0, s>>>(a);
+    else if (nv <= 4) head_token_kernel<4><<<hgrid, 256, 0, s>>>(a);
+    else if (nv <= 6) head_token_kernel<6><<<hgrid, 256, 0, s>>>(a);
+    else if (nv <= 8) head_token_kernel<8><<<hgrid, 256, 0, s>>>(a);
+    else head_token_kernel<16><<<hgrid, 256, 0, s>>>(a);
     check_launch("head_token");
     {
         const long long total = (long long)a.nb * a.C * a.S * a.S;
