@@ -825,12 +825,16 @@ int pdm_debug_linear(const float* A, const float* A2, const float* W, const floa
         cudaStream_t s = (cudaStream_t)stream;
         const int Kt = K + (A2 ? K2 : 0);
         GemmProblem g;
-        g.K1 = K; g.K2 = A2 ? K2 : 0; g.N = N; g.nb = 1; g.Lr = M; g.bias = bias; g.resid = resid; g.gelu = gelu != 0;
+        g.K1 = K; g.K2 = A2 ? K2 : 0; g.N = N; g.nb = 1; g.Lr = M; g.bias = bias; g.gelu = gelu != 0;
         g.out32 = out;
+        if (resid) {  // the production kernels update the fp32 residual stream in place
+            PDM_CHECK_CUDA(cudaMemcpyAsync(out, resid, (size_t)M * N * sizeof(float), cudaMemcpyDeviceToDevice, s));
+            g.resid = out;
+        }
         if (precision == PDM_PREC_FP32) {
             g.A1 = A; g.A2 = A2; g.W32 = W;
             gemm_simt_f32(g, s);
-            time_kernel([&] { gemm_simt_f32(g, s); }, resid ? 0 : iters, ms, s);
+            time_kernel([&] { gemm_simt_f32(g, s); }, iters, ms, s);
         } else {
             DevBuf a16((size_t)M * K * 2), a216((size_t)M * (A2 ? K2 : 0) * 2), w16((size_t)N * Kt * 2);
             convert_f32_bf16(A, (bf16*)a16.p, (long long)M * K, s);

@@ -1,15 +1,21 @@
 // tcgen05 / TMEM / TMA bf16 GEMM with fused epilogue for sm_100a.
 //
-//   out = [gelu]( [A1 | A2] . W^T + bias ) [+ resid]      (libs/uvit_t2i.py:69,90,179; libs/timm.py:106-110)
+//   out = [gelu]( [A1 | A2] . W^T + bias ) [+= into fp32 out]     (libs/uvit_t2i.py:69,90,179; libs/timm.py:106-110)
 //
-// Persistent, warp-specialised, one CTA per SM:
-//   warp 0      TMA producer   (A via 3-D map [K, rows, batch], W via 2-D map [K, N]; SWIZZLE_128B)
-//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x 256 x 16, fp32 accumulate)
-//   warps 2..9  epilogue: tcgen05.ld -> per-warp smem transpose -> coalesced 128-bit global I/O
-// Pipelines: STAGES-deep smem ring (full/empty mbarriers) and a 2-deep TMEM accumulator ring
-// (2 x 256 columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
-// The long-skip concat (uvit_t2i.py:179) is never materialised: the K loop streams A1 then A2 through
-// two tensor maps.  Row views (two-stream zero-conv on mx[:, :334]) use the batch coordinate of the map.
+// Persistent, warp-specialised.  NCTA = 2 (default): CTA pairs (cta_group::2) compute 256x256 tiles with UMMA M=256;
+// each CTA stages its own 128 rows of A and only HALF of the W tile, halving L2->SM and shared-memory operand
+// traffic per MMA.  NCTA = 1: one CTA per 128x256 tile (kept for A/B measurement, PDM_GEMM_1CTA=1).
+//   warp 0      TMA producer (A through a 3-D map [K, rows, batch]; W through a map [K, N]; SWIZZLE_128B);
+//               in pair mode completion bytes of both CTAs are credited to the leader's full barrier
+//   warp 1      TMEM allocator; (leader) one thread issues tcgen05.mma and commits: smem slot free / accumulator full
+//               (multicast to both CTAs in pair mode)
+//   warps 2..9  epilogue on the CTA's own 128 accumulator rows: tcgen05.ld -> per-warp smem transpose ->
+//               coalesced 128-bit global I/O.  All global loads the epilogue needs (bias, the fp32 residual tile)
+//               are issued BEFORE the accumulator is waited for / one chunk ahead, so their latency hides behind
+//               the MMAs.  bf16-only outputs are packed before the transpose (half the smem traffic).
+// Rings: STAGES-deep smem ring, 2-deep TMEM accumulator ring (2 x 256 columns).
+// The long-skip concat is never materialised (K loop streams A1 then A2); row views use the map's batch coordinate.
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -18,28 +24,40 @@
 #include "ptx.cuh"
 
 namespace pdm {
+
+CUtensorMap make_tmap_bf16_3d(const void* ptr, long long K, long long rows, long long nbatch, long long bs,
+                              int box_rows, int box_k);
+
 namespace {
 
-constexpr int BM = 128, BN = 256, BK = 64, STAGES = 3;
+constexpr int BM = 128;  // accumulator rows per CTA
+constexpr int BN = 256, BK = 64;
 constexpr int EPI_WARPS = 8;
 constexpr int THREADS = 64 + EPI_WARPS * 32;
 constexpr int A_BYTES = BM * BK * 2;
-constexpr int B_BYTES = BN * BK * 2;
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int SCR_STRIDE = 36;  // floats per scratch row (32 + 4 pad, keeps 16 B alignment, conflict-free)
-constexpr int SCR_BYTES = 32 * SCR_STRIDE * 4;
-constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + EPI_WARPS * SCR_BYTES + 256 /*barriers*/;
+constexpr int SCR_STRIDE = 36;  // 32-bit words per scratch row: 128 B payload + 16 B pad (16 B aligned, conflict-free)
+constexpr int SCR_WORDS = 32 * SCR_STRIDE + 128;  // + 128 floats: this warp's slice of the bias vector
+constexpr int SCR_BYTES = SCR_WORDS * 4;
 constexpr uint32_t TMEM_COLS = 512;
+
+template <int NCTA>
+struct Cfg {
+    static constexpr int B_BYTES = (BN / NCTA) * BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = NCTA == 2 ? 5 : 3;
+    static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + EPI_WARPS * SCR_BYTES + 256;
+};
 
 struct TcParams {
     int KB1, KB;  // k-blocks taken from A1, total k-blocks
-    int N, Lr, tpb, ntn, total_tiles;
+    int N, Lr, tpb, ntn;
+    int n_mtiles;     // 128-row tiles over all batches
+    int total_tiles;  // scheduler tiles = ceil(n_mtiles / NCTA) * ntn
     const float* bias;
-    const float* resid;
-    long long resid_bs;
-    float* out32;
+    float* out32;     // fp32 output (nullptr: none)
     long long out32_bs;
-    bf16* out2;
+    int accumulate;   // out32 += (residual stream update in place)
+    bf16* out2;       // bf16 output (nullptr: none)
     long long out2_bs;
     int gelu;
 };
@@ -48,7 +66,7 @@ struct TcParams {
 // with (a, b, c) fitted to the exact erf form: max abs deviation 3.1e-5 on [-8, 8] (the textbook 2-term tanh form is
 // 4.7e-4); tanh.approx adds <= 2^-11 relative.  Both are far below the bf16 rounding of the stored activation.
 // 7 FMA-pipe ops + 1 MUFU per element instead of erff's ~25: the fc1 epilogue stays under the MMA time.
-__device__ __forceinline__ float gelu_erf(float x) {
+__device__ __forceinline__ float gelu_fast(float x) {
     const float u = fminf(x * x, 64.f);
     const float w = x * fmaf(u, fmaf(u, -3.56580544e-04f, 3.70435562e-02f), 7.97452612e-01f);
     float t;
@@ -56,43 +74,72 @@ __device__ __forceinline__ float gelu_erf(float x) {
     const float hx = 0.5f * x;
     return fmaf(hx, t, hx);
 }
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
 
-__global__ void __launch_bounds__(THREADS, 1)
+template <int NCTA>
+__device__ __forceinline__ void release_accumulator(uint64_t* tempty_bar, uint32_t rank, int lane) {
+    ptx::tc_fence_before();
+    __syncwarp();
+    if (lane == 0) {
+        if (NCTA == 1 || rank == 0) ptx::mbar_arrive(tempty_bar);
+        else ptx::mbar_arrive_remote(tempty_bar, 0);
+    }
+}
+
+template <int NCTA>
+__global__ void __cluster_dims__(NCTA, 1, 1) __launch_bounds__(THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+    using C = Cfg<NCTA>;
+    constexpr int STAGES = C::STAGES;
+    constexpr int STAGE_BYTES = C::STAGE_BYTES;
     extern __shared__ uint8_t smem_raw[];
+    // identical offsets in both CTAs of a pair (the dynamic smem window starts at the same offset in every CTA)
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* scr_base = smem + STAGES * STAGE_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(scr_base + EPI_WARPS * SCR_BYTES);
-    uint64_t* full = bars;                     // [STAGES]
-    uint64_t* empty = bars + STAGES;           // [STAGES]
-    uint64_t* tfull = bars + 2 * STAGES;       // [2]
-    uint64_t* tempty = bars + 2 * STAGES + 2;  // [2]
+    uint64_t* full = bars;                     // [STAGES]  waited on by the (leader's) MMA thread
+    uint64_t* empty = bars + STAGES;           // [STAGES]  each CTA its own; MMA commit (multicast)
+    uint64_t* tfull = bars + 2 * STAGES;       // [2]       each CTA its own; MMA commit (multicast)
+    uint64_t* tempty = bars + 2 * STAGES + 2;  // [2]       leader's; all epilogue warps of the pair arrive
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const uint32_t rank = NCTA == 2 ? ptx::cluster_ctarank() : 0u;
+    const int unit_id = blockIdx.x / NCTA;     // scheduling unit: CTA or CTA pair
+    const int n_units = gridDim.x / NCTA;
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&tmA1);
         ptx::prefetch_tmap(&tmA2);
         ptx::prefetch_tmap(&tmB);
         for (int i = 0; i < STAGES; ++i) {
+            // ONE arrive (leader's producer, carrying the byte count of all CTAs' loads); the peer only contributes
+            // complete_tx bytes.  (A remote arrive per k-block costs a cluster-scope release: measured 23 % tensor.)
             ptx::mbar_init(&full[i], 1);
             ptx::mbar_init(&empty[i], 1);
         }
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&tfull[i], 1);
-            ptx::mbar_init(&tempty[i], EPI_WARPS);
+            ptx::mbar_init(&tempty[i], NCTA * EPI_WARPS);
         }
         ptx::fence_mbar_init();
     }
     if (warp == 1) {
-        ptx::tmem_alloc(tmem_slot, TMEM_COLS);
-        ptx::tmem_relinquish();
+        if (NCTA == 2) {
+            ptx::tmem_alloc_2sm(tmem_slot, TMEM_COLS);
+            ptx::tmem_relinquish_2sm();
+        } else {
+            ptx::tmem_alloc(tmem_slot, TMEM_COLS);
+            ptx::tmem_relinquish();
+        }
     }
     ptx::tc_fence_before();
-    __syncthreads();
+    if (NCTA == 2) ptx::cluster_sync(); else __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -101,19 +148,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-                const int mt = tile / p.ntn, nt = tile - mt * p.ntn;
-                const int b = mt / p.tpb, t0 = (mt - b * p.tpb) * BM;
+            for (int tile = unit_id; tile < p.total_tiles; tile += n_units) {
+                const int mp = tile / p.ntn, nt = tile - mp * p.ntn;
+                const int mt = NCTA * mp + (int)rank;       // this CTA's 128-row tile
+                int b = 0, t0 = p.tpb * BM;                 // padding tile: fully out of bounds -> zero fill
+                if (mt < p.n_mtiles) {
+                    b = mt / p.tpb;
+                    t0 = (mt - b * p.tpb) * BM;
+                }
+                const int n0 = nt * BN + (int)rank * (BN / NCTA);
                 for (int kb = 0; kb < p.KB; ++kb) {
                     ptx::mbar_wait(&empty[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * STAGE_BYTES;
                     uint8_t* sb = sa + A_BYTES;
-                    ptx::mbar_expect_tx(&full[stage], STAGE_BYTES);
-                    if (kb < p.KB1)
-                        ptx::tma_load_3d(&tmA1, &full[stage], sa, kb * BK, t0, b);
-                    else
-                        ptx::tma_load_3d(&tmA2, &full[stage], sa, (kb - p.KB1) * BK, t0, b);
-                    ptx::tma_load_3d(&tmB, &full[stage], sb, kb * BK, nt * BN, 0);
+                    if (rank == 0) ptx::mbar_expect_tx(&full[stage], NCTA * STAGE_BYTES);
+                    const CUtensorMap* ta = kb < p.KB1 ? &tmA1 : &tmA2;
+                    const int ka = (kb < p.KB1 ? kb : kb - p.KB1) * BK;
+                    if (NCTA == 2) {
+                        ptx::tma_load_3d_2sm(ta, &full[stage], sa, ka, t0, b);
+                        ptx::tma_load_3d_2sm(&tmB, &full[stage], sb, kb * BK, n0, 0);
+                    } else {
+                        ptx::tma_load_3d(ta, &full[stage], sa, ka, t0, b);
+                        ptx::tma_load_3d(&tmB, &full[stage], sb, kb * BK, n0, 0);
+                    }
                     if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1;
@@ -122,13 +179,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer (one thread) =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc = ptx::make_idesc_bf16(BM, BN);
+        // ===================== MMA issuer (leader CTA, one thread) =====================
+        if (rank == 0 && lane == 0) {
+            constexpr uint32_t idesc = ptx::make_idesc_bf16(NCTA * BM, BN);
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+            for (int tile = unit_id; tile < p.total_tiles; tile += n_units, ++it) {
                 const int as = it & 1;
                 const uint32_t aphase = (it >> 1) & 1;
                 ptx::mbar_wait(&tempty[as], aphase ^ 1);
@@ -143,111 +200,164 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {
                         // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle row
-                        ptx::mma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                        if (NCTA == 2) ptx::mma_bf16_ss_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                        else ptx::mma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
                     }
-                    ptx::mma_commit(&empty[stage]);  // frees the smem slot when these MMAs retire
+                    if (NCTA == 2) ptx::mma_commit_2sm(&empty[stage], 3); else ptx::mma_commit(&empty[stage]);
                     if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1;
                     }
                 }
-                ptx::mma_commit(&tfull[as]);  // accumulator ready for the epilogue
+                if (NCTA == 2) ptx::mma_commit_2sm(&tfull[as], 3); else ptx::mma_commit(&tfull[as]);
             }
         }
     } else {
-        // ===================== epilogue =====================
+        // ===================== epilogue (own 128 rows) =====================
         const int ew = warp - 2;
-        const int q = warp & 3;   // TMEM lane quarter this warp may access
-        const int half = ew >> 2; // which 128-column half of the tile
-        float* scr = reinterpret_cast<float*>(scr_base + ew * SCR_BYTES);
-        const int rsub = lane >> 3, c4 = lane & 7;
+        const int q = warp & 3;    // TMEM lane quarter this warp may access
+        const int half = ew >> 2;  // which 128-column half of the tile
+        uint32_t* scr = reinterpret_cast<uint32_t*>(scr_base + ew * SCR_BYTES);
+        float* sbias = reinterpret_cast<float*>(scr + 32 * SCR_STRIDE);  // [128]
+        const bool packed = (p.out32 == nullptr) && ((p.N & 7) == 0);
+        const int rsub = lane >> 3, c8 = lane & 7;
         int it = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-            const int mt = tile / p.ntn, nt = tile - mt * p.ntn;
-            const int b = mt / p.tpb, t0 = (mt - b * p.tpb) * BM;
+        for (int tile = unit_id; tile < p.total_tiles; tile += n_units, ++it) {
+            const int mp = tile / p.ntn, nt = tile - mp * p.ntn;
+            const int mt = NCTA * mp + (int)rank;
+            const bool tile_ok = mt < p.n_mtiles;
+            const int b = tile_ok ? mt / p.tpb : 0;
+            const int t0 = tile_ok ? (mt - b * p.tpb) * BM : 0;
+            const int lr_eff = tile_ok ? p.Lr : 0;  // no row is valid in a padding tile
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
-            ptx::mbar_wait(&tfull[as], aphase);
-            ptx::tc_fence_after();
-            const int trow0 = t0 + q * 32;  // first token row handled by this warp
-#pragma unroll 1
-            for (int chunk = 0; chunk < 4; ++chunk) {
-                const int col0 = half * 128 + chunk * 32;
-                uint32_t v[32];
-                ptx::tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + as * BN + col0, v);
-                ptx::tmem_ld_wait();
-                if (chunk == 3) {
-                    // all TMEM reads of this warp for this accumulator are done: hand it back to the MMA warp
-                    ptx::tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive(&tempty[as]);
-                }
-                const int col = nt * BN + col0 + c4 * 4;
-                const bool col_ok = col < p.N;
-                // prefetch the residual rows while the transpose goes through shared memory
-                float4 res[8];
-                if (p.resid) {
+            const int trow0 = t0 + q * 32;
+            const int ncol0 = nt * BN + half * 128;  // first column of this warp's slice
+            const uint32_t tbase = tmem_base + (uint32_t(q * 32) << 16) + as * BN + half * 128;
+            if (packed) {
+                // ---- bf16-only output: 2 chunks of 64 columns; bias/GELU in the row domain, pack, transpose ----
+                if (p.bias) {
 #pragma unroll
-                    for (int ps = 0; ps < 8; ++ps) {
-                        const int t = trow0 + ps * 4 + rsub;
-                        res[ps] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (col_ok && t < p.Lr)
-                            res[ps] = *reinterpret_cast<const float4*>(p.resid + ((long long)b * p.resid_bs + t) * p.N + col);
+                    for (int i = 0; i < 4; ++i) {
+                        const int c = ncol0 + lane + 32 * i;
+                        sbias[lane + 32 * i] = c < p.N ? __ldg(p.bias + c) : 0.f;
                     }
-                }
-                float* srow = scr + lane * SCR_STRIDE;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    *reinterpret_cast<float4*>(srow + 4 * j) =
-                        make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                    __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
                 }
                 __syncwarp();
-                float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (p.bias && col_ok) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+                ptx::mbar_wait(&tfull[as], aphase);
+                ptx::tc_fence_after();
+#pragma unroll 1
+                for (int chunk = 0; chunk < 2; ++chunk) {
+                    uint32_t* srow = scr + lane * SCR_STRIDE;
 #pragma unroll
-                for (int ps = 0; ps < 8; ++ps) {
-                    const int r = ps * 4 + rsub;
-                    const int t = trow0 + r;
-                    float4 a = *reinterpret_cast<const float4*>(scr + r * SCR_STRIDE + c4 * 4);
-                    a.x += bias4.x;
-                    a.y += bias4.y;
-                    a.z += bias4.z;
-                    a.w += bias4.w;
-                    if (p.gelu) {
-                        a.x = gelu_erf(a.x);
-                        a.y = gelu_erf(a.y);
-                        a.z = gelu_erf(a.z);
-                        a.w = gelu_erf(a.w);
-                    }
-                    if (p.resid) {
-                        a.x += res[ps].x;
-                        a.y += res[ps].y;
-                        a.z += res[ps].z;
-                        a.w += res[ps].w;
-                    }
-                    if (col_ok && t < p.Lr) {
-                        if (p.out32)
-                            *reinterpret_cast<float4*>(p.out32 + ((long long)b * p.out32_bs + t) * p.N + col) = a;
-                        if (p.out2) {
-                            __nv_bfloat162 lo = __floats2bfloat162_rn(a.x, a.y), hi = __floats2bfloat162_rn(a.z, a.w);
-                            uint2 pk;
-                            pk.x = *reinterpret_cast<uint32_t*>(&lo);
-                            pk.y = *reinterpret_cast<uint32_t*>(&hi);
-                            *reinterpret_cast<uint2*>(p.out2 + ((long long)b * p.out2_bs + t) * p.N + col) = pk;
+                    for (int hh = 0; hh < 2; ++hh) {
+                        uint32_t v[32];
+                        ptx::tmem_ld_32x32(tbase + chunk * 64 + hh * 32, v);
+                        ptx::tmem_ld_wait();
+                        if (chunk == 1 && hh == 1) release_accumulator<NCTA>(&tempty[as], rank, lane);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            float f[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[8 * j + e]);
+                            if (p.bias) {
+                                const float4 b0 = *reinterpret_cast<const float4*>(sbias + chunk * 64 + hh * 32 + 8 * j);
+                                const float4 b1 = *reinterpret_cast<const float4*>(sbias + chunk * 64 + hh * 32 + 8 * j + 4);
+                                f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+                                f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+                            }
+                            if (p.gelu) {
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) f[e] = gelu_fast(f[e]);
+                            }
+                            *reinterpret_cast<uint4*>(srow + (hh * 4 + j) * 4) =
+                                make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
                         }
                     }
+                    __syncwarp();
+                    const int col = ncol0 + chunk * 64 + c8 * 8;
+                    bf16* orow = p.out2 + ((long long)b * p.out2_bs + trow0 + rsub) * p.N + col;
+                    const long long rstep = 4LL * p.N;
+#pragma unroll
+                    for (int ps = 0; ps < 8; ++ps) {
+                        const int r = ps * 4 + rsub;
+                        const uint4 val = *reinterpret_cast<const uint4*>(scr + r * SCR_STRIDE + c8 * 4);
+                        if (col < p.N && trow0 + r < lr_eff) *reinterpret_cast<uint4*>(orow) = val;
+                        orow += rstep;
+                    }
+                    __syncwarp();
                 }
-                __syncwarp();
+            } else {
+                // ---- fp32 output (optionally += in place): 4 chunks of 32 columns through an fp32 transpose ----
+                const int colq = ncol0 + c8 * 4;  // this lane's 4 columns inside chunk 0
+                const long long rstep = 4LL * p.N;
+                float* o32 = p.out32 + ((long long)b * p.out32_bs + trow0 + rsub) * p.N + colq;
+                bf16* o16 = p.out2 ? p.out2 + ((long long)b * p.out2_bs + trow0 + rsub) * p.N + colq : nullptr;
+                float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);  // bias of the current chunk (next one is prefetched)
+                if (p.bias && colq < p.N) bb = __ldg(reinterpret_cast<const float4*>(p.bias + colq));
+                // residual rows of chunk 0, fetched before the accumulator is even ready
+                float4 res[8];
+                if (p.accumulate) {
+#pragma unroll
+                    for (int ps = 0; ps < 8; ++ps) {
+                        res[ps] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (colq < p.N && trow0 + ps * 4 + rsub < lr_eff)
+                            res[ps] = *reinterpret_cast<const float4*>(o32 + ps * rstep);
+                    }
+                }
+                ptx::mbar_wait(&tfull[as], aphase);
+                ptx::tc_fence_after();
+#pragma unroll 1
+                for (int chunk = 0; chunk < 4; ++chunk) {
+                    uint32_t v[32];
+                    ptx::tmem_ld_32x32(tbase + chunk * 32, v);
+                    ptx::tmem_ld_wait();
+                    if (chunk == 3) release_accumulator<NCTA>(&tempty[as], rank, lane);
+                    uint32_t* srow = scr + lane * SCR_STRIDE;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        *reinterpret_cast<uint4*>(srow + 4 * j) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    __syncwarp();
+                    const int col = colq + 32 * chunk;
+                    const bool col_ok = col < p.N;
+                    const bool next_ok = chunk < 3 && col + 32 < p.N;
+                    float4 bb_next = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (p.bias && next_ok) bb_next = __ldg(reinterpret_cast<const float4*>(p.bias + col + 32));
+                    float* po = o32 + 32 * chunk;
+                    bf16* ph = o16 ? o16 + 32 * chunk : nullptr;
+#pragma unroll
+                    for (int ps = 0; ps < 8; ++ps) {
+                        const int r = ps * 4 + rsub;
+                        const bool row_ok = trow0 + r < lr_eff;
+                        float4 a = *reinterpret_cast<const float4*>(scr + r * SCR_STRIDE + c8 * 4);
+                        a.x += bb.x; a.y += bb.y; a.z += bb.z; a.w += bb.w;
+                        if (p.gelu) {
+                            a.x = gelu_fast(a.x); a.y = gelu_fast(a.y); a.z = gelu_fast(a.z); a.w = gelu_fast(a.w);
+                        }
+                        if (p.accumulate) {
+                            a.x += res[ps].x; a.y += res[ps].y; a.z += res[ps].z; a.w += res[ps].w;
+                            // software pipeline: fetch the same row of the NEXT chunk into the slot just consumed
+                            if (next_ok && row_ok) res[ps] = *reinterpret_cast<const float4*>(po + 32);
+                        }
+                        if (col_ok && row_ok) {
+                            *reinterpret_cast<float4*>(po) = a;
+                            if (ph) *reinterpret_cast<uint2*>(ph) = make_uint2(pack2(a.x, a.y), pack2(a.z, a.w));
+                        }
+                        po += rstep;
+                        if (ph) ph += rstep;
+                    }
+                    bb = bb_next;
+                    __syncwarp();
+                }
             }
         }
     }
 
     ptx::tc_fence_before();
-    __syncthreads();
+    if (NCTA == 2) ptx::cluster_sync(); else __syncthreads();
     if (warp == 1) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+        if (NCTA == 2) ptx::tmem_dealloc_2sm(tmem_base, TMEM_COLS); else ptx::tmem_dealloc(tmem_base, TMEM_COLS);
     }
 }
 
@@ -275,9 +385,54 @@ typedef std::tuple<const void*, long long, long long, long long, long long, int,
 std::map<MapKey, CUtensorMap> g_map_cache;
 std::mutex g_map_mutex;
 
+int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        PDM_CHECK_CUDA(cudaGetDevice(&dev));
+        PDM_CHECK_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+    }
+    return n;
+}
+
+template <int NCTA>
+void launch(const GemmProblem& g, cudaStream_t s) {
+    const int K2 = g.A2 ? g.K2 : 0;
+    const int K = g.K1 + K2;
+    TcParams p;
+    p.KB1 = ceil_div(g.K1, BK);
+    p.KB = p.KB1 + ceil_div(K2, BK);
+    p.N = g.N;
+    p.Lr = g.Lr;
+    p.tpb = ceil_div(g.Lr, BM);
+    p.ntn = ceil_div(g.N, BN);
+    p.n_mtiles = g.nb * p.tpb;
+    p.total_tiles = ceil_div(p.n_mtiles, NCTA) * p.ntn;
+    p.bias = g.bias;
+    p.out32 = g.out32;
+    p.out32_bs = g.out32_bs ? g.out32_bs : g.Lr;
+    p.accumulate = g.resid != nullptr;
+    p.out2 = (bf16*)g.out2;
+    p.out2_bs = g.out2_bs ? g.out2_bs : g.Lr;
+    p.gelu = g.gelu ? 1 : 0;
+    const CUtensorMap tmA1 = make_tmap_bf16_3d(g.A1, g.K1, g.Lr, g.nb, g.a1_bs ? g.a1_bs : g.Lr, BM, BK);
+    const CUtensorMap tmA2 =
+        g.A2 ? make_tmap_bf16_3d(g.A2, g.K2, g.Lr, g.nb, g.a2_bs ? g.a2_bs : g.Lr, BM, BK) : tmA1;
+    const CUtensorMap tmB = make_tmap_bf16_3d(g.W16, K, g.N, 1, g.N, BN / NCTA, BK);
+    static bool attr_set = false;
+    if (!attr_set) {
+        PDM_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<NCTA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            Cfg<NCTA>::SMEM_BYTES));
+        attr_set = true;
+    }
+    const int units = std::max(1, std::min(p.total_tiles, num_sms() / NCTA));
+    gemm_tc_kernel<NCTA><<<NCTA * units, THREADS, Cfg<NCTA>::SMEM_BYTES, s>>>(tmA1, tmA2, tmB, p);
+    check_launch("gemm_tc");
+}
+
 }  // namespace
 
-// bf16 [nbatch][rows][K] view with batch stride bs rows; box = [64 (K), box_rows, 1]; SWIZZLE_128B
+// bf16 [nbatch][rows][K] view with batch stride bs rows; box = [box_k (K), box_rows, 1]; SWIZZLE_128B
 CUtensorMap make_tmap_bf16_3d(const void* ptr, long long K, long long rows, long long nbatch, long long bs,
                               int box_rows, int box_k) {
     MapKey key(ptr, K, rows, nbatch, bs, box_rows, box_k);
@@ -307,50 +462,15 @@ void clear_tmap_cache() {
     g_map_cache.clear();
 }
 
-static int g_num_sms = 0;
-static int num_sms() {
-    if (g_num_sms == 0) {
-        int dev = 0;
-        PDM_CHECK_CUDA(cudaGetDevice(&dev));
-        PDM_CHECK_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-    }
-    return g_num_sms;
-}
-
 void gemm_tc_bf16(const GemmProblem& g, cudaStream_t s) {
     PDM_REQUIRE(g.A1 && g.W16 && g.Lr > 0 && g.nb > 0, "gemm_tc: bad problem");
     PDM_REQUIRE(g.N % 4 == 0, "gemm_tc: N must be a multiple of 4");
     PDM_REQUIRE(g.K1 % 8 == 0 && (!g.A2 || (g.K1 % BK == 0 && g.K2 % 8 == 0)), "gemm_tc: K alignment");
-    const int K2 = g.A2 ? g.K2 : 0;
-    const int K = g.K1 + K2;
-    TcParams p;
-    p.KB1 = ceil_div(g.K1, BK);
-    p.KB = p.KB1 + ceil_div(K2, BK);
-    p.N = g.N;
-    p.Lr = g.Lr;
-    p.tpb = ceil_div(g.Lr, BM);
-    p.ntn = ceil_div(g.N, BN);
-    p.total_tiles = g.nb * p.tpb * p.ntn;
-    p.bias = g.bias;
-    p.resid = g.resid;
-    p.resid_bs = g.resid_bs ? g.resid_bs : g.Lr;
-    p.out32 = g.out32;
-    p.out32_bs = g.out32_bs ? g.out32_bs : g.Lr;
-    p.out2 = (bf16*)g.out2;
-    p.out2_bs = g.out2_bs ? g.out2_bs : g.Lr;
-    p.gelu = g.gelu ? 1 : 0;
-    const CUtensorMap tmA1 = make_tmap_bf16_3d(g.A1, g.K1, g.Lr, g.nb, g.a1_bs ? g.a1_bs : g.Lr, BM, BK);
-    const CUtensorMap tmA2 =
-        g.A2 ? make_tmap_bf16_3d(g.A2, g.K2, g.Lr, g.nb, g.a2_bs ? g.a2_bs : g.Lr, BM, BK) : tmA1;
-    const CUtensorMap tmB = make_tmap_bf16_3d(g.W16, K, g.N, 1, g.N, BN, BK);
-    static bool attr_set = false;
-    if (!attr_set) {
-        PDM_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        attr_set = true;
-    }
-    const int grid = std::min(p.total_tiles, num_sms());
-    gemm_tc_kernel<<<grid, THREADS, SMEM_BYTES, s>>>(tmA1, tmA2, tmB, p);
-    check_launch("gemm_tc");
+    PDM_REQUIRE(g.out32 || g.out2, "gemm_tc: no output");
+    PDM_REQUIRE(!g.resid || (g.resid == g.out32 && (g.resid_bs ? g.resid_bs : g.Lr) == (g.out32_bs ? g.out32_bs : g.Lr)),
+                "gemm_tc: the residual must be the fp32 output (in-place accumulate)");
+    static const bool one_cta = getenv("PDM_GEMM_1CTA") != nullptr;
+    if (one_cta) launch<1>(g, s); else launch<2>(g, s);
 }
 
 }  // namespace pdm
