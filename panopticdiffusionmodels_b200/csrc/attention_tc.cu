@@ -11,6 +11,7 @@
 //            from TMEM and folded into the fp32 register accumulator with the online-softmax rescale.
 // 2 CTAs are resident per SM (112 KB smem, 256 TMEM columns each), so one CTA's softmax overlaps the
 // other's MMAs.
+#include <cstdlib>
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -40,7 +41,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 }
 
 __global__ void __launch_bounds__(THREADS, 2)
-attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__ out, int L, int H) {
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__ out, int L, int H, int dbg) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* sQ = smem;
     uint8_t* sK = smem + TILE_BYTES;          // [2]
@@ -141,9 +142,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict_
             ptx::mbar_wait(s_full, j & 1);
             ptx::tc_fence_after();
             // pass 1: row max
-            float mx = -INFINITY;
+            float mx = (dbg & 1) ? 8.f : -INFINITY;
 #pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < ((dbg & 1) ? 0 : 4); ++c) {
                 uint32_t v[32];
                 ptx::tmem_ld_32x32(tmem_base + lane_base + S_COL + c * 32, v);
                 ptx::tmem_ld_wait();
@@ -189,7 +190,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict_
             ptx::mbar_wait(o_full, j & 1);
             ptx::tc_fence_after();
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
+            for (int c = 0; c < ((dbg & 2) ? 0 : 2); ++c) {
                 uint32_t v[32];
                 ptx::tmem_ld_32x32(tmem_base + lane_base + O_COL + c * 32, v);
                 ptx::tmem_ld_wait();
@@ -223,7 +224,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict_
 
 }  // namespace
 
-void attention_tc_bf16(const bf16* qkv, bf16* out, int nb, int L, int H, cudaStream_t s) {
+void attention_tc_v1(const bf16* qkv, bf16* out, int nb, int L, int H, cudaStream_t s) {
     const int D = H * HD;
     const CUtensorMap tm = make_tmap_bf16_3d(qkv, 3LL * D, L, nb, L, 128, HD);
     static bool attr_set = false;
@@ -232,7 +233,8 @@ void attention_tc_bf16(const bf16* qkv, bf16* out, int nb, int L, int H, cudaStr
         attr_set = true;
     }
     dim3 grid(ceil_div(L, QT), H, nb);
-    attention_tc_kernel<<<grid, THREADS, SMEM_BYTES, s>>>(tm, out, L, H);
+    static const int dbg = getenv("PDM_ATTN_DBG") ? atoi(getenv("PDM_ATTN_DBG")) : 0;
+    attention_tc_kernel<<<grid, THREADS, SMEM_BYTES, s>>>(tm, out, L, H, dbg);
     check_launch("attention_tc");
 }
 

@@ -74,6 +74,34 @@ __device__ __forceinline__ float gelu_fast(float x) {
     const float hx = 0.5f * x;
     return fmaf(hx, t, hx);
 }
+// two lanes at once with the packed fp32x2 FMA-pipe ops of sm_100 (FFMA2 / FMUL2): 5 instructions per element pair less
+__device__ __forceinline__ void gelu_fast2(float& x0, float& x1) {
+    uint64_t x, u, w, hx, r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(x0), "f"(x1));
+    asm("mul.rn.f32x2 %0, %1, %1;" : "=l"(u) : "l"(x));
+    float u0, u1;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(u0), "=f"(u1) : "l"(u));
+    u0 = fminf(u0, 64.f);
+    u1 = fminf(u1, 64.f);
+    asm("mov.b64 %0, {%1, %2};" : "=l"(u) : "f"(u0), "f"(u1));
+    uint64_t ca, cb, cc, half;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(cc) : "f"(-3.56580544e-04f));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(cb) : "f"(3.70435562e-02f));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(ca) : "f"(7.97452612e-01f));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(half) : "f"(0.5f));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(w) : "l"(u), "l"(cc), "l"(cb));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(w) : "l"(u), "l"(w), "l"(ca));
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(w) : "l"(w), "l"(x));
+    float w0, w1, t0, t1;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(w0), "=f"(w1) : "l"(w));
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(w0));
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(w1));
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(hx) : "l"(x), "l"(half));
+    uint64_t t;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(t) : "f"(t0), "f"(t1));
+    asm("fma.rn.f32x2 %0, %1, %2, %1;" : "=l"(r) : "l"(hx), "l"(t));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(r));
+}
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&v);
@@ -268,7 +296,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
                             }
                             if (p.gelu) {
 #pragma unroll
-                                for (int e = 0; e < 8; ++e) f[e] = gelu_fast(f[e]);
+                                for (int e = 0; e < 8; e += 2) gelu_fast2(f[e], f[e + 1]);
                             }
                             *reinterpret_cast<uint4*>(srow + (hh * 4 + j) * 4) =
                                 make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
