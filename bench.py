@@ -71,6 +71,15 @@ def peaks():
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
 
 
+def gemm_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    `ncu --set full` capture (profiles/r01_gemm_ncu_summary.md); None when no capture is committed."""
+    p = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
+    if not os.path.exists(p):
+        return None
+    return json.load(open(p)).get("dram_bytes_per_launch_mean")
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -282,7 +291,7 @@ def run_ours(a):
         roof = {"kernel": "gemm_tc_kernel (tcgen05 bf16 GEMM: qkv/proj/fc1/fc2/skip/zero-conv)", "bound": "tensor",
                 "achieved": round(ach, 1), "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": round(ach / pk["tf_sust"], 4),
                 "peak_src": pk["src"] + " (sustained bf16)", "launches": g_n, "avg_launch_ms": round(g_ms / g_n, 4),
-                "flops_per_launch": gemm_flops / g_n, "share_of_step": round(g_ms / tot, 4), "traffic": None}
+                "flops_per_launch": gemm_flops / g_n, "share_of_step": round(g_ms / tot, 4), "traffic": gemm_traffic()}
 
     if rank == 0:
         cb = None if a.no_cpu_baseline else cpu_eval_rate(kw, a.nfe, a.scale, steps=1, warmup=1)

@@ -99,6 +99,18 @@ int pdm_cfg_update(const float* eps_c, const float* eps_u, const float* pm_c, co
                    const float* m_base, float* P0, float* m_out,
                    const float* coef, float cfg_scale, int64_t n_img, int64_t n_mask, void* stream);
 
+/* replaces: dpm_multistep_update / dpm_multistep_second_update / dpm_multistep_third_update (dpm_solver_pp.py:602-677,
+ * 852-871; data prediction, solver_type='dpm_solver') fused with the guidance combine and eps->x0, ONE kernel per step.
+ * `coef` (HOST, PDM_PLAN_STRIDE floats): [0] t_model [1] alpha(t_0) [2] sigma(t_0) [3] A=sigma_t/sigma_0 [4] B
+ * [5] C1 [6] C2 [7] 1/r0 [8] 1/r1 [9] r0/(r0+r1) [10] 1/(r0+r1) [11] order (1,2,3) [12] 0.5*B.
+ *   x: state the network was evaluated at (t_0); X1/X2: cached data predictions at t_-1/t_-2 (NULL if order is lower);
+ *   X0 (out): data prediction at t_0; x_out: state at t.  The mask stream (m, P1, P2 -> P0, m_out) gets the same
+ *   update with the mask prediction as its data prediction (no reference behaviour exists: parity unpinned). */
+int pdm_multistep_update(const float* eps_c, const float* eps_u, const float* pm_c, const float* pm_u, const float* x,
+                         const float* X1, const float* X2, float* X0, float* x_out, const float* m, const float* P1,
+                         const float* P2, float* P0, float* m_out, const float* coef, float cfg_scale, int64_t n_img,
+                         int64_t n_mask, void* stream);
+
 /* replaces: DPM_Solver.sample(method='fast') (dpm_solver_pp.py:1018-1044) driven by cfg_nnet
  * (train_t2i_discrete.py:387-439, 506-516): the whole denoising loop on the device.
  *   plan: HOST array [n_evals][PDM_PLAN_STRIDE] built by the host planner (solver scalars are data

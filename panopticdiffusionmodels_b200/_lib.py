@@ -35,6 +35,7 @@ SIGNATURES = {
     "pdm_nnet_forward": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P]),
     "pdm_cfg_update": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(C.c_float), C.c_float,
                                  C.c_int64, C.c_int64, _P]),
+    "pdm_multistep_update": (C.c_int, [_P] * 14 + [C.POINTER(C.c_float), C.c_float, C.c_int64, C.c_int64, _P]),
     "pdm_sample": (C.c_int, [_P, C.POINTER(C.c_float), C.c_int32, _P, _P, _P, _P, C.c_float, _P, _P, C.c_int32,
                              C.c_int32, C.c_int32, _P]),
     "pdm_bits2int": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, _P]),

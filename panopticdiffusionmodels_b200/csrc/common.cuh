@@ -150,6 +150,27 @@ struct UpdateArgs {
 };
 void cfg_solver_update(const UpdateArgs& a, cudaStream_t s);
 
+struct MultistepArgs {
+    const float* eps_c;
+    const float* eps_u;
+    const float* pm_c;
+    const float* pm_u;
+    const float* x;       // state the network was evaluated at (time t_0)
+    const float* X1;      // data prediction at t_{-1}
+    const float* X2;      // data prediction at t_{-2}
+    float* X0;            // out: data prediction at t_0
+    float* x_out;
+    const float* m;
+    const float* P1;
+    const float* P2;
+    float* P0;
+    float* m_out;
+    float alpha, sigma, A, B, C1, C2, inv_r0, inv_r1, q, inv_r01, halfB, scale;
+    int order;
+    long long n_img, n_mask;
+};
+void multistep_update(const MultistepArgs& a, cudaStream_t s);
+
 void bits2int(const float* pm, int32_t* labels, int B, int nbits, int hw, cudaStream_t s);
 void int2bits(const int32_t* ids, float* bits, int B, int nbits, int hw, cudaStream_t s);
 

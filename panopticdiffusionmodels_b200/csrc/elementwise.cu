@@ -488,6 +488,63 @@ void cfg_solver_update(const UpdateArgs& a, cudaStream_t s) {
 }
 
 // ----------------------------------------------------------------------------------------------
+// Multistep DPM-Solver++ 2M / 3M (dpm_solver_pp.py:602-677, data prediction, solver_type='dpm_solver'), fused with
+// the CFG combine and eps -> x0 like K12.  Operation order of the reference:
+//   1 : x_t = A x + B X0                                   (dpm_solver_first_update with the cached prediction)
+//   2M: D1_0 = (1/r0)(X0 - X1);  x_t = A x - B X0 - (0.5 B) D1_0
+//   3M: D1_1 = (1/r1)(X1 - X2);  d = D1_0 - D1_1;  D1 = D1_0 + q d;  D2 = (1/(r0+r1)) d
+//       x_t = A x - B X0 + C1 D1 - C2 D2
+// The mask stream gets the same update with the mask prediction as its data prediction (no reference behaviour
+// exists for it -- SURVEY F2 -- so that sub-case is "parity unpinned").
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ float ms_update(float x, float X0, float X1, float X2, const MultistepArgs& a) {
+    if (a.order == 1) return __fadd_rn(__fmul_rn(a.A, x), __fmul_rn(a.B, X0));
+    const float base = __fsub_rn(__fmul_rn(a.A, x), __fmul_rn(a.B, X0));
+    const float D10 = __fmul_rn(a.inv_r0, __fsub_rn(X0, X1));
+    if (a.order == 2) return __fsub_rn(base, __fmul_rn(a.halfB, D10));
+    const float D11 = __fmul_rn(a.inv_r1, __fsub_rn(X1, X2));
+    const float d = __fsub_rn(D10, D11);
+    const float D1 = __fadd_rn(D10, __fmul_rn(a.q, d));
+    const float D2 = __fmul_rn(a.inv_r01, d);
+    return __fsub_rn(__fadd_rn(base, __fmul_rn(a.C1, D1)), __fmul_rn(a.C2, D2));
+}
+
+__global__ void __launch_bounds__(256) multistep_kernel(MultistepArgs a) {
+    const long long n = a.n_img + a.n_mask;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        if (i < a.n_img) {
+            const float c = a.eps_c[i];
+            float e = c;
+            if (a.eps_u) e = __fadd_rn(c, __fmul_rn(a.scale, __fsub_rn(c, a.eps_u[i])));
+            const float x = a.x[i];
+            const float X0 = __fdiv_rn(__fsub_rn(x, __fmul_rn(a.sigma, e)), a.alpha);
+            const float X1 = a.order >= 2 ? a.X1[i] : 0.f, X2 = a.order >= 3 ? a.X2[i] : 0.f;
+            a.X0[i] = X0;
+            a.x_out[i] = ms_update(x, X0, X1, X2, a);
+        } else {
+            const long long j = i - a.n_img;
+            const float c = a.pm_c[j];
+            float P0 = c;
+            if (a.pm_u) P0 = __fadd_rn(c, __fmul_rn(a.scale, __fsub_rn(c, a.pm_u[j])));
+            const float P1 = a.order >= 2 ? a.P1[j] : 0.f, P2 = a.order >= 3 ? a.P2[j] : 0.f;
+            a.P0[j] = P0;
+            a.m_out[j] = ms_update(a.m[j], P0, P1, P2, a);
+        }
+    }
+}
+
+void multistep_update(const MultistepArgs& a, cudaStream_t s) {
+    PDM_REQUIRE(a.order >= 1 && a.order <= 3, "multistep: order must be 1, 2 or 3");
+    PDM_REQUIRE(a.n_mask == 0 || (a.pm_c && a.m && a.P0 && a.m_out), "multistep: mask pointers missing");
+    const long long n = a.n_img + a.n_mask;
+    const int grid = (int)std::max<long long>(1, std::min<long long>(ceil_div_ll(n, 256), 148 * 8));
+    multistep_kernel<<<grid, 256, 0, s>>>(a);
+    check_launch("multistep_update");
+}
+
+// ----------------------------------------------------------------------------------------------
 // analog-bit codec (utils.py:475-518): MSB first.
 // ----------------------------------------------------------------------------------------------
 __global__ void bits2int_kernel(const float* __restrict__ pm, int32_t* __restrict__ labels, int B, int nbits, int hw) {

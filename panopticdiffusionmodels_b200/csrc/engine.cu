@@ -804,6 +804,24 @@ int pdm_sample(pdm_handle h, const float* plan, int32_t n_evals, const float* z_
     });
 }
 
+int pdm_multistep_update(const float* eps_c, const float* eps_u, const float* pm_c, const float* pm_u, const float* x,
+                         const float* X1, const float* X2, float* X0, float* x_out, const float* m, const float* P1,
+                         const float* P2, float* P0, float* m_out, const float* coef, float cfg_scale, int64_t n_img,
+                         int64_t n_mask, void* stream) {
+    return guard([&] {
+        PDM_REQUIRE(eps_c && x && X0 && x_out && coef, "null argument");
+        MultistepArgs a;
+        a.eps_c = eps_c; a.eps_u = eps_u; a.pm_c = pm_c; a.pm_u = pm_u; a.x = x; a.X1 = X1; a.X2 = X2; a.X0 = X0;
+        a.x_out = x_out; a.m = m; a.P1 = P1; a.P2 = P2; a.P0 = P0; a.m_out = m_out;
+        a.alpha = coef[1]; a.sigma = coef[2]; a.A = coef[3]; a.B = coef[4]; a.C1 = coef[5]; a.C2 = coef[6];
+        a.inv_r0 = coef[7]; a.inv_r1 = coef[8]; a.q = coef[9]; a.inv_r01 = coef[10]; a.order = (int)coef[11];
+        a.halfB = coef[12]; a.scale = cfg_scale; a.n_img = n_img; a.n_mask = pm_c ? n_mask : 0;
+        PDM_REQUIRE(a.order < 2 || X1, "multistep: X1 required for order >= 2");
+        PDM_REQUIRE(a.order < 3 || X2, "multistep: X2 required for order 3");
+        multistep_update(a, (cudaStream_t)stream);
+    });
+}
+
 int pdm_bits2int(const float* pred_mask, int32_t* labels, int32_t B, int32_t nbits, int32_t hw, void* stream) {
     return guard([&] {
         PDM_REQUIRE(pred_mask && labels, "null argument");

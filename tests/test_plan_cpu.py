@@ -98,3 +98,29 @@ def test_plan_image_only():
     ns = P.NoiseScheduleVP("discrete", betas=dpm_oracle.sd_betas())
     z, _ = emulate_plan(P.build_plan(ns, 8, 3, eps=1e-3, T=1.0), model, g["x"], None)
     assert torch.equal(z, z_ref)
+
+
+def test_multistep_plan_matches_reference_updates():
+    """multistep_record + the kernel's operation order (emulated with torch float32) == the reference's
+    dpm_multistep_second/third_update outputs stored in tests/golden/multistep.npz (bit exact)."""
+    from panopticdiffusionmodels_b200.multistep import build_multistep_plan, multistep_record
+    g, _ = load_golden("multistep.npz")
+    ns = P.NoiseScheduleVP("discrete", betas=dpm_oracle.sd_betas())
+    f = lambda v: torch.tensor(float(v), dtype=torch.float32)
+    t = [g["t"][i] for i in range(4)]
+    x, X2, X1, X0 = g["x"], g["X2"], g["X1"], g["X0"]
+    rec = multistep_record(ns, t[:3], t[3])
+    assert rec[11] == 3
+    A, B, C1, C2, ir0, ir1, q, ir01 = (f(rec[i]) for i in (3, 4, 5, 6, 7, 8, 9, 10))
+    D10 = ir0 * (X0 - X1)
+    D11 = ir1 * (X1 - X2)
+    d = D10 - D11
+    out3 = A * x - B * X0 + C1 * (D10 + q * d) - C2 * (ir01 * d)
+    assert torch.equal(out3, g["m3"])
+    rec = multistep_record(ns, t[1:3], t[3])
+    assert rec[11] == 2
+    A, B, ir0, hB = (f(rec[i]) for i in (3, 4, 7, 12))
+    out2 = A * x - B * X0 - hB * (ir0 * (X0 - X1))
+    assert torch.equal(out2, g["m2"])
+    plan = build_multistep_plan(ns, 10, 3, eps=1e-3, T=1.0, skip_type="time_uniform")
+    assert plan.shape == (10, P.PLAN_STRIDE) and list(plan[:4, 11]) == [1, 2, 3, 3] and plan[0, 0] == 1000.0
