@@ -205,22 +205,19 @@ def run_ours(a):
     out_host_z = torch.empty(B, 4, S, S).pin_memory()
     out_host_m = torch.empty(B, 8, S, S).pin_memory()
 
+    from panopticdiffusionmodels_b200.distributed import gather_samples
+
     def step_resident():
         z, pm = js.sample(d_ctx, d_empty, z_init=d_z, mask_init=d_m)
-        if world > 1:  # the path's one exchange: all-gather of finished latents + mask predictions
-            gz = torch.empty(world * B, 4, S, S, device=dev)
-            gm = torch.empty(world * B, 8, S, S, device=dev)
-            dist.all_gather_into_tensor(gz, z)
-            dist.all_gather_into_tensor(gm, pm)
-            return gz, gm
-        return z, pm
+        return gather_samples(z, pm)  # the path's one exchange: NCCL all-gather of finished latents + mask predictions
 
     def step_e2e():
         c, e = h_ctx.to(dev, non_blocking=True), h_empty.to(dev, non_blocking=True)
         z0, m0 = h_z.to(dev, non_blocking=True), h_m.to(dev, non_blocking=True)
         z, pm = js.sample(c, e, z_init=z0, mask_init=m0)
-        out_host_z.copy_(z, non_blocking=True)
-        out_host_m.copy_(pm, non_blocking=True)
+        gz, gm = gather_samples(z, pm)
+        out_host_z.copy_(gz[rank * B:(rank + 1) * B], non_blocking=True)
+        out_host_m.copy_(gm[rank * B:(rank + 1) * B], non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
     def timed(fn, steps):
