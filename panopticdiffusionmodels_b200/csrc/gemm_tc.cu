@@ -126,7 +126,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     constexpr int STAGE_BYTES = C::STAGE_BYTES;
     extern __shared__ uint8_t smem_raw[];
     // identical offsets in both CTAs of a pair (the dynamic smem window starts at the same offset in every CTA)
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // (pointer arithmetic on the __shared__ array, not an integer round trip, so the compiler keeps the shared address
+    //  space: an earlier version went through uintptr_t and every scratch access became a generic LD/ST on the long
+    //  scoreboard)
+    uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* scr_base = smem + STAGES * STAGE_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(scr_base + EPI_WARPS * SCR_BYTES);
     uint64_t* full = bars;                     // [STAGES]  waited on by the (leader's) MMA thread

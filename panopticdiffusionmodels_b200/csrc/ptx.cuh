@@ -54,6 +54,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
     }
 }
+// wait with back-off: for roles that are far ahead of their consumer (TMA producers with a full ring), so that the
+// spinning single-thread warp does not steal issue slots from the compute warps on its SM sub-partition
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) __nanosleep(64);
+}
 
 // ---------------- TMA ----------------
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
