@@ -10,7 +10,7 @@ import os
 from typing import Optional
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpdm.so")
+LIB_PATH = os.environ.get("PDM_LIB") or os.path.join(HERE, "libpdm.so")  # PDM_LIB: development override
 
 PREC_BF16 = 0
 PREC_FP32 = 1

@@ -18,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libpdm.so")
-SOURCES = ["elementwise.cu", "gemm_simt.cu", "gemm_tc.cu", "attention_simt.cu", "attention_tc.cu", "attention_tc2.cu", "engine.cu"]
+SOURCES = ["elementwise.cu", "gemm_simt.cu", "gemm_tc.cu", "attention_simt.cu", "attention_tc.cu", "attention_tc2.cu", "attention_tc3.cu", "engine.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",
@@ -43,16 +43,17 @@ def _digest(paths) -> str:
 
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ, exist_ok=True)
+    extra = os.environ.get("PDM_NVCC_EXTRA", "").split()  # development switches, e.g. -DPDM_ATTN_TRACE
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "pdm.h")]
     stamp = os.path.join(OBJ, "stamp.txt")
-    digest = _digest(deps)
+    digest = _digest(deps) + " ".join(extra)
     if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == digest:
         return LIB
     nvcc = _nvcc()
 
     def compile_one(src):
         obj = os.path.join(OBJ, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")

@@ -32,6 +32,9 @@ def main():
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--prec", type=int, default=0)
+    ap.add_argument("--only", default="", help="comma list: gemm,layernorm,attention")
+    ap.add_argument("--attn-nb", type=int, default=0, help="attention batch rows (default min(2*batch, 64))")
+    ap.add_argument("--attn-L", type=int, default=0)
     a = ap.parse_args()
     D, H, L = SHAPES[a.config]
     M = 2 * a.batch * L
@@ -57,23 +60,29 @@ def main():
         print(json.dumps(out[-1]), flush=True)
         del A, A2, W, o, r
 
-    gemm("gemm_qkv", 3 * D, D)
-    gemm("gemm_proj(+resid)", D, D, resid=True)
-    gemm("gemm_fc1(+gelu)", 4 * D, D, gelu=1)
-    gemm("gemm_fc2(+resid)", D, 4 * D, resid=True)
-    gemm("gemm_skip", D, D, K2=D)
+    only = set(a.only.split(",")) if a.only else {"gemm", "layernorm", "attention"}
+    if "gemm" in only:
+        gemm("gemm_qkv", 3 * D, D)
+        gemm("gemm_proj(+resid)", D, D, resid=True)
+        gemm("gemm_fc1(+gelu)", 4 * D, D, gelu=1)
+        gemm("gemm_fc2(+resid)", D, 4 * D, resid=True)
+        gemm("gemm_skip", D, D, K2=D)
 
-    x = torch.randn(M, D, device=dev)
-    w = torch.randn(D, device=dev)
-    o = torch.empty(M, D, device=dev)
-    _lib.check(lib.pdm_debug_layernorm(_lib.ptr(x), _lib.ptr(w), _lib.ptr(w), _lib.ptr(o), M, D, a.prec, a.iters,
-                                       C.byref(ms), s))
-    by = M * D * (4 + (2 if a.prec == 0 else 4))
-    print(json.dumps(dict(kernel="layernorm", rows=M, D=D, ms=round(ms.value, 4), gbs=round(by / ms.value / 1e6, 1),
-                          frac_of_hbm_peak=round(by / ms.value / 1e6 / hbm, 3), peak_src=src)), flush=True)
-    del x, o
+    if "layernorm" in only:
+        x = torch.randn(M, D, device=dev)
+        w = torch.randn(D, device=dev)
+        o = torch.empty(M, D, device=dev)
+        _lib.check(lib.pdm_debug_layernorm(_lib.ptr(x), _lib.ptr(w), _lib.ptr(w), _lib.ptr(o), M, D, a.prec, a.iters,
+                                           C.byref(ms), s))
+        by = M * D * (4 + (2 if a.prec == 0 else 4))
+        print(json.dumps(dict(kernel="layernorm", rows=M, D=D, ms=round(ms.value, 4), gbs=round(by / ms.value / 1e6, 1),
+                              frac_of_hbm_peak=round(by / ms.value / 1e6 / hbm, 3), peak_src=src)), flush=True)
+        del x, o
+    if "attention" not in only:
+        return
 
-    nb = min(2 * a.batch, 64)
+    nb = a.attn_nb or min(2 * a.batch, 64)
+    L = a.attn_L or L
     qkv = torch.randn(nb, L, 3 * D, device=dev)
     o = torch.empty(nb, L, D, device=dev)
     _lib.check(lib.pdm_debug_attention(_lib.ptr(qkv), _lib.ptr(o), nb, L, H, a.prec, max(1, a.iters // 3), C.byref(ms), s))
