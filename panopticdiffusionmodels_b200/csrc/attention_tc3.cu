@@ -5,20 +5,22 @@
 //     "same"  items: two consecutive query tiles of one (row, head) -- both tiles share every K/V tile;
 //     "split" items: the ragged last query tile of head 2i paired with the ragged last tile of head 2i+1
 //                    (own K/V tiles each), so an odd tile count (L = 590 -> 5, L = 334 -> 3) costs no idle slot.
-// Tensor memory (512 columns): S0 | S1 | S2 (3 x 128 fp32 columns, ROTATING over the sequence of tile-steps)
-//                              O_a | O_b    (2 x 64).   P (bf16) overwrites the first 64 columns of its S buffer.
-// With three S buffers for two tiles, Q.K^T of a tile-step is issued (and finished) long before its softmax
-// warpgroup gets there: the exp2 phases of the two warpgroups run back to back on the MUFU pipe, which is the
-// bound for head_dim 64 (16 ex2/clk/SM vs 32 scores/clk/SM of MMA).
-//   warps 0-3 / 4-7   softmax warpgroups a / b, one query row per thread: whole S row -> registers, row max, lazy
-//                     rescale (only when a row max outgrew its reference by > 2^8), exp2, P -> TMEM (tcgen05.st).
-//                     Chunks of 32 keys beyond L are skipped, warps whose 32 query rows are all >= L do nothing.
+// Tensor memory (512 columns), per tile slot t in {a, b}:  S_t (128 fp32 columns) | P_t (64 columns = 128 bf16) |
+// O_t (64 fp32 columns).  A softmax warpgroup pulls the WHOLE S row into registers first and releases S_t at once
+// (s_free), so Q.K^T of the next key tile runs under the exp2 phase of the current one -- the register file is the
+// second S buffer; nothing on the tensor pipe waits for a softmax except P.V itself.
+//   warps 0-3 / 4-7   softmax warpgroups a / b, one query row per thread: S row -> registers, row max, lazy rescale
+//                     (only when a row max outgrew its reference by > 2^8), exp2 (MUFU, plus an FMA-pipe polynomial
+//                     for a fixed quarter of the scores: the MUFU pipe, 16 ex2/clk/SM, is this kernel's bound),
+//                     P -> TMEM (tcgen05.st).  Chunks of 32 keys beyond L are skipped; warps whose 32 query rows are
+//                     all >= L do nothing.  The O epilogue of an item is deferred under the next item's first tile.
 //   warp 8            TMA producer: Q tiles (double-buffered across items) and a 5-slot ring of (K | V) tiles, all
 //                     straight out of the packed qkv activation [nb, L, 3D] via one 3-D tensor map.
-//   warp 9            one thread issues S = Q.K^T (UMMA 128 x N x 16, N = 128 or the ragged tail rounded to 16) and
-//                     O += P.V (UMMA 128 x 64 x 16, A = P from TMEM, B = V MN-major as it lies in memory), keeping
-//                     Q.K^T up to three tile-steps ahead of P.V -- across item boundaries too, so the prologue and
-//                     the O epilogue of an item are hidden under its neighbours.
+//   warp 9 / 10       issue O_t += P_t.V (UMMA 128 x 64 x 16, A = P from TMEM, B = V MN-major as it lies in memory)
+//                     and S_t = Q.K^T (UMMA 128 x N x 16, N = 128 or the ragged tail rounded to 16).  The whole warp
+//                     walks the schedule (uniform registers), one elected lane issues.
+// Barrier discipline: a parity wait is only meaningful while the waiter is at most one phase away from the barrier,
+// so every waiter consumes EVERY phase of the barriers it uses, in order.
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -45,13 +47,12 @@ int sm_count() {
 constexpr int QT = 128, KT = 128, HD = 64;
 constexpr int TILE_BYTES = 128 * HD * 2;  // 16 KB
 constexpr int NSLOT = 5;                  // K/V ring slots, (K tile | V tile) each
-constexpr int NSBUF = 3;                  // rotating S buffers
 constexpr int Q_BYTES = 4 * TILE_BYTES;   // 2 item slots x 2 tiles
 constexpr int BAR_BYTES = 256;
 constexpr int SMEM_BYTES = 1024 + Q_BYTES + NSLOT * 2 * TILE_BYTES + BAR_BYTES;
 constexpr int THREADS = 384;  // warps 0-7 softmax, 8 TMA, 9 P.V, 10 Q.K^T, 11 idle (setmaxnreg works on whole warpgroups)
 constexpr uint32_t TMEM_COLS = 512;
-constexpr uint32_t O_COL = 384;  // + t * 64;  S buffer i at column i * 128
+constexpr uint32_t S_COL = 0, P_COL = 256, O_COL = 384;  // + t * {128, 64, 64}
 constexpr float RESCALE_LOG2 = 8.f;
 
 __device__ __forceinline__ float ex2(float x) {
@@ -98,23 +99,49 @@ struct Item {
     int b, hA, hB, qA, qB, nt;  // nt = number of live tiles (0: nothing to do)
     bool same;
 };
-__device__ __forceinline__ Item decode_item(const Shape& sh, int it) {
-    Item I;
-    const int unit = it / sh.ipu, r = it - unit * sh.ipu;
-    I.b = unit / sh.H2;
-    const int hp = unit - I.b * sh.H2;
-    const int h0 = 2 * hp, h1 = 2 * hp + 1;
-    const bool h1ok = h1 < sh.H;
-    if (r < sh.fp) {
-        I.hA = I.hB = h0; I.qA = 2 * r; I.qB = 2 * r + 1; I.nt = 2; I.same = true;
-    } else if (sh.odd && r == sh.fp) {
-        I.hA = h0; I.hB = h1; I.qA = I.qB = sh.nq - 1; I.nt = h1ok ? 2 : 1; I.same = false;
-    } else {
-        const int r2 = r - sh.fp - sh.odd;
-        I.hA = I.hB = h1; I.qA = 2 * r2; I.qB = 2 * r2 + 1; I.nt = h1ok ? 2 : 0; I.same = true;
+// Walks the items blockIdx.x, blockIdx.x + gridDim.x, ... ; the (row, head pair, index in unit) coordinates advance
+// incrementally (three divisions once, none per item).
+struct ItemWalk {
+    int it, b, hp, r;
+    int d_r, d_hp, d_b;
+    __device__ __forceinline__ void init(const Shape& sh) {
+        it = blockIdx.x;
+        const int unit = it / sh.ipu;
+        r = it - unit * sh.ipu;
+        b = unit / sh.H2;
+        hp = unit - b * sh.H2;
+        const int g = gridDim.x, du = g / sh.ipu;
+        d_r = g - du * sh.ipu;
+        d_b = du / sh.H2;
+        d_hp = du - d_b * sh.H2;
     }
-    return I;
-}
+    __device__ __forceinline__ void next(const Shape& sh) {
+        it += gridDim.x;
+        r += d_r;
+        int c = 0;
+        if (r >= sh.ipu) { r -= sh.ipu; c = 1; }
+        hp += d_hp + c;
+        c = 0;
+        if (hp >= sh.H2) { hp -= sh.H2; c = 1; }
+        b += d_b + c;
+    }
+    __device__ __forceinline__ bool done(const Shape& sh) const { return it >= sh.n_items; }
+    __device__ __forceinline__ Item get(const Shape& sh) const {
+        Item I;
+        I.b = b;
+        const int h0 = 2 * hp, h1 = 2 * hp + 1;
+        const bool h1ok = h1 < sh.H;
+        if (r < sh.fp) {
+            I.hA = I.hB = h0; I.qA = 2 * r; I.qB = 2 * r + 1; I.nt = 2; I.same = true;
+        } else if (sh.odd && r == sh.fp) {
+            I.hA = h0; I.hB = h1; I.qA = I.qB = sh.nq - 1; I.nt = h1ok ? 2 : 1; I.same = false;
+        } else {
+            const int r2 = r - sh.fp - sh.odd;
+            I.hA = I.hB = h1; I.qA = 2 * r2; I.qB = 2 * r2 + 1; I.nt = h1ok ? 2 : 0; I.same = true;
+        }
+        return I;
+    }
+};
 
 struct Ring {  // position in the K/V slot ring
     int slot = NSLOT - 1;
@@ -140,17 +167,46 @@ __device__ __forceinline__ void trace_ev(int ev, uint32_t n, int& cnt) {
 #define TRACE(ev, n)
 #endif
 
-// One key tile of one query row: S row (NCH chunks of 32 fp32 columns at s_addr) -> registers, row max, lazy rescale
-// of the O row, p = exp2((s - m_ref) * scale * log2 e) -> bf16 P written over the first NCH*16 columns of the S buffer.
+// exp2 on the FMA pipe: Cody-Waite split x = n + f with the round-to-nearest magic-number add, 2^f on [-0.5, 0.5] by a
+// degree-3 minimax polynomial (max relative error 7.5e-5, 25x below the bf16 rounding of P), 2^n by an integer add
+// into the exponent field.  Packed f32x2 arithmetic.
+#ifndef PDM_ATTN_POLY_PAIRS
+#define PDM_ATTN_POLY_PAIRS 0x8888  // which of the 16 pairs of a 32-key chunk take the FMA-pipe path (4 of 16)
+#endif
+constexpr uint32_t POLY_PAIRS = PDM_ATTN_POLY_PAIRS;
+__device__ __forceinline__ void exp2_poly2(float a0, float a1, float& p0, float& p1) {
+    a0 = fmaxf(a0, -126.f);  // below: exponent underflow of the integer add
+    a1 = fmaxf(a1, -126.f);
+    const uint64_t a2 = pack_f2(a0, a1);
+    const uint64_t t2 = add2(a2, pack_f2(12582912.f, 12582912.f));      // 1.5 * 2^23: low mantissa bits = round(a)
+    const uint64_t n2 = add2(t2, pack_f2(-12582912.f, -12582912.f));    // round(a) as float
+    const uint64_t f2 = fma2(n2, pack_f2(-1.f, -1.f), a2);              // f = a - round(a)
+    uint64_t q2 = fma2(pack_f2(0.055171646f, 0.055171646f), f2, pack_f2(0.24261113f, 0.24261113f));
+    q2 = fma2(q2, f2, pack_f2(0.69326097f, 0.69326097f));
+    q2 = fma2(q2, f2, pack_f2(0.99992806f, 0.99992806f));
+    float t0, t1, q0, q1;
+    unpack_f2(t2, t0, t1);
+    unpack_f2(q2, q0, q1);
+    p0 = __uint_as_float(__float_as_uint(q0) + (__float_as_uint(t0) << 23));
+    p1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(t1) << 23));
+}
+
+// One key tile of one query row: S row (NCH chunks of 32 fp32 columns at s_addr) -> registers (then S is handed back:
+// s_free), row max, lazy rescale of the O row, p = exp2((s - m_ref) * scale * log2 e) -> bf16 P at p_addr.
 // MASK: keys >= nvalid of the last chunk count as -inf.
+// wait_prev: the previous P.V of this tile slot (which read P_t and wrote O_t) must have completed (o_full parity).
 template <int NCH, bool MASK>
-__device__ __forceinline__ void softmax_tile(uint32_t s_addr, uint32_t o_addr, int nvalid, bool first, float& m_ref,
-                                             float& l, uint64_t* o_full_bar, uint32_t o_full_parity) {
+__device__ __forceinline__ void softmax_tile(uint32_t s_addr, uint32_t p_addr, uint32_t o_addr, int nvalid, bool first,
+                                             bool wait_prev, float& m_ref, float& l, uint64_t* s_free_bar,
+                                             uint64_t* o_full_bar, uint32_t o_full_parity, int lane) {
     const float cs = 0.125f * 1.4426950408889634f;  // softmax scale * log2(e)
     uint32_t s[NCH][32];
 #pragma unroll
     for (int c = 0; c < NCH; ++c) ptx::tmem_ld_32x32(s_addr + c * 32, s[c]);
     ptx::tmem_ld_wait();
+    ptx::tc_fence_before();
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(s_free_bar);  // the next Q.K^T of this tile slot may overwrite S now
     if (MASK) {
 #pragma unroll
         for (int i = 0; i < 32; ++i)
@@ -165,18 +221,16 @@ __device__ __forceinline__ void softmax_tile(uint32_t s_addr, uint32_t o_addr, i
             mxb = max3(mxb, __uint_as_float(s[c][i + 2]), __uint_as_float(s[c][i + 3]));
         }
     const float mx = fmaxf(mxa, mxb);
+    if (wait_prev) {
+        ptx::mbar_wait(o_full_bar, o_full_parity);  // completed long ago, normally
+        ptx::tc_fence_after();
+    }
     if (first) {
         m_ref = mx;
-    } else {
-        // P.V of the previous key tile has landed in O (long ago, normally).  Every warp consumes EVERY phase of
-        // o_full in order: a parity wait is only meaningful while the waiter is at most one phase away.
-        ptx::mbar_wait(o_full_bar, o_full_parity);
-    }
-    if (!first && __any_sync(0xffffffffu, (mx - m_ref) * cs > RESCALE_LOG2)) {
+    } else if (__any_sync(0xffffffffu, (mx - m_ref) * cs > RESCALE_LOG2)) {
         // rare: some row outgrew its reference by more than 2^8: rescale l and the O rows accumulated so far
         const float m_new = fmaxf(m_ref, mx);
         const float corr = ex2((m_ref - m_new) * cs);
-        ptx::tc_fence_after();
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
             uint32_t o[32];
@@ -197,19 +251,23 @@ __device__ __forceinline__ void softmax_tile(uint32_t s_addr, uint32_t o_addr, i
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-            float a0, a1;
+            float a0, a1, p0, p1;
             unpack_f2(fma2(pack_f2(__uint_as_float(s[c][2 * i]), __uint_as_float(s[c][2 * i + 1])), cs2, nmb2), a0, a1);
-            const float p0 = ex2(a0), p1 = ex2(a1);
+            if (!MASK && ((POLY_PAIRS >> i) & 1)) {
+                exp2_poly2(a0, a1, p0, p1);  // FMA-pipe exp2 for a fixed subset of the pairs: unloads the MUFU pipe
+            } else {
+                p0 = ex2(a0);
+                p1 = ex2(a1);
+            }
             if (i & 1) lb = add2(lb, pack_f2(p0, p1)); else la = add2(la, pack_f2(p0, p1));
             pk[i] = pack_bf16(p0, p1);
         }
-        ptx::tmem_st_32x32_x16(s_addr + c * 16, pk);  // P overwrites S (the whole S row is in registers)
+        ptx::tmem_st_32x32_x16(p_addr + c * 16, pk);
     }
     float x0, x1;
     unpack_f2(add2(la, lb), x0, x1);
     l += x0 + x1;
 }
-
 
 __global__ void __launch_bounds__(THREADS, 1)
 attention_tc3_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__ out, const Shape sh) {
@@ -218,16 +276,16 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict
     uint8_t* sQ = smem;               // [2 item slots][2 tiles]
     uint8_t* sKV = smem + Q_BYTES;    // [NSLOT] x (K tile | V tile)
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Q_BYTES + NSLOT * 2 * TILE_BYTES);
-    uint64_t* q_full = bars;                  // [2]
-    uint64_t* q_empty = bars + 2;             // [2]
-    uint64_t* kv_full = bars + 4;             // [NSLOT]
-    uint64_t* kv_empty = bars + 4 + NSLOT;    // [NSLOT]
-    uint64_t* s_full = bars + 4 + 2 * NSLOT;  // [NSBUF]
-    uint64_t* p_full = s_full + NSBUF;        // [NSBUF]
-    uint64_t* o_full = p_full + NSBUF;        // [2]
-    uint64_t* o_empty = o_full + 2;           // [2]
-    uint64_t* s_free = o_empty + 2;           // [NSBUF]  P.V done with the P in S buffer i
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + NSBUF);
+    uint64_t* q_full = bars;                  // [2]      TMA -> Q.K^T warp
+    uint64_t* q_empty = bars + 2;             // [2]      Q.K^T commit -> TMA
+    uint64_t* kv_full = bars + 4;             // [NSLOT]  TMA -> Q.K^T warp (P.V follows in program order of the data flow)
+    uint64_t* kv_empty = bars + 4 + NSLOT;    // [NSLOT]  P.V commit -> TMA
+    uint64_t* s_full = bars + 4 + 2 * NSLOT;  // [2]      Q.K^T commit -> softmax warpgroup t
+    uint64_t* s_free = s_full + 2;            // [2]      softmax warpgroup t (4 warps) -> Q.K^T warp: S_t is in registers
+    uint64_t* p_full = s_free + 2;            // [2]      softmax warpgroup t (4 warps) -> P.V warp
+    uint64_t* o_full = p_full + 2;            // [2]      P.V commit -> softmax warpgroup t (P_t consumed, O_t updated)
+    uint64_t* o_empty = o_full + 2;           // [2]      softmax warpgroup t (4 warps) -> P.V warp: O_t drained
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int D = sh.H * HD;
@@ -241,17 +299,15 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&q_full[i], 1);
             ptx::mbar_init(&q_empty[i], 1);
+            ptx::mbar_init(&s_full[i], 1);
+            ptx::mbar_init(&s_free[i], 4);
+            ptx::mbar_init(&p_full[i], 4);
             ptx::mbar_init(&o_full[i], 1);
             ptx::mbar_init(&o_empty[i], 4);
         }
         for (int i = 0; i < NSLOT; ++i) {
             ptx::mbar_init(&kv_full[i], 1);
             ptx::mbar_init(&kv_empty[i], 1);
-        }
-        for (int i = 0; i < NSBUF; ++i) {
-            ptx::mbar_init(&s_full[i], 1);
-            ptx::mbar_init(&p_full[i], 4);
-            ptx::mbar_init(&s_free[i], 1);
         }
         ptx::fence_mbar_init();
     }
@@ -266,146 +322,136 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict
 
     if (warp >= 8) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        // Producer and MMA warps: the WHOLE warp walks the schedule (warp-uniform control flow and operands, so the
+        // descriptors live in uniform registers); only the TMA / tcgen05.mma / tcgen05.commit instructions are issued
+        // by one elected lane.  (A single-lane region makes the compiler wrap every such instruction in a
+        // uniformisation loop of ~17 dependent instructions: ~100 clk per MMA, which starved the tensor pipe.)
+        const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+        const uint32_t sQ_u = __shfl_sync(0xffffffffu, ptx::smem_u32(sQ), 0);
+        const uint32_t sKV_u = __shfl_sync(0xffffffffu, ptx::smem_u32(sKV), 0);
+        ItemWalk w;
+        w.init(sh);
         if (warp == 8) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
+            // ===================== TMA producer =====================
             Ring ring;
             int qi = 0;
-            for (int it = blockIdx.x; it < sh.n_items; it += gridDim.x) {
-                const Item I = decode_item(sh, it);
+            for (; !w.done(sh); w.next(sh)) {
+                const Item I = w.get(sh);
                 if (I.nt == 0) continue;
                 const int qs = qi & 1;
                 ptx::mbar_wait_relaxed(&q_empty[qs], ((qi >> 1) & 1) ^ 1);
-                ptx::mbar_expect_tx(&q_full[qs], I.nt * TILE_BYTES);
-                ptx::tma_load_3d(&tmQKV, &q_full[qs], sQ + qs * 2 * TILE_BYTES, I.hA * HD, I.qA * QT, I.b);
-                if (I.nt == 2)
-                    ptx::tma_load_3d(&tmQKV, &q_full[qs], sQ + qs * 2 * TILE_BYTES + TILE_BYTES, I.hB * HD, I.qB * QT, I.b);
+                if (ptx::elect_one()) {
+                    ptx::mbar_expect_tx(&q_full[qs], I.nt * TILE_BYTES);
+                    ptx::tma_load_3d(&tmQKV, &q_full[qs], sQ_u + qs * 2 * TILE_BYTES, I.hA * HD, I.qA * QT, I.b);
+                    if (I.nt == 2)
+                        ptx::tma_load_3d(&tmQKV, &q_full[qs], sQ_u + qs * 2 * TILE_BYTES + TILE_BYTES, I.hB * HD, I.qB * QT, I.b);
+                }
+                __syncwarp();
                 const int nsrc = (I.nt == 2 && !I.same) ? 2 : 1;
                 for (int j = 0; j < nkv; ++j) {
                     for (int u = 0; u < nsrc; ++u) {
                         const int h = u ? I.hB : I.hA;
                         ring.next();
                         ptx::mbar_wait_relaxed(&kv_empty[ring.slot], ring.ph ^ 1);
-                        uint8_t* sk = sKV + ring.slot * 2 * TILE_BYTES;
-                        ptx::mbar_expect_tx(&kv_full[ring.slot], 2 * TILE_BYTES);
-                        ptx::tma_load_3d(&tmQKV, &kv_full[ring.slot], sk, D + h * HD, j * KT, I.b);
-                        ptx::tma_load_3d(&tmQKV, &kv_full[ring.slot], sk + TILE_BYTES, 2 * D + h * HD, j * KT, I.b);
+                        const uint32_t sk = sKV_u + ring.slot * 2 * TILE_BYTES;
+                        if (ptx::elect_one()) {
+                            ptx::mbar_expect_tx(&kv_full[ring.slot], 2 * TILE_BYTES);
+                            ptx::tma_load_3d(&tmQKV, &kv_full[ring.slot], sk, D + h * HD, j * KT, I.b);
+                            ptx::tma_load_3d(&tmQKV, &kv_full[ring.slot], sk + TILE_BYTES, 2 * D + h * HD, j * KT, I.b);
+                        }
+                        __syncwarp();
                     }
                 }
                 ++qi;
             }
-        }
-        } else if (warp == 9 || warp == 10) {
-            // ===================== MMA issuers: warp 9 issues O += P.V, warp 10 issues S = Q.K^T =====================
-            // The WHOLE warp walks the schedule (warp-uniform control flow and operands, so the descriptors live in
-            // uniform registers); only the tcgen05.mma / tcgen05.commit instructions themselves are issued by one
-            // elected lane.  (A single-lane region makes the compiler wrap every MMA in a uniformisation loop of
-            // ~17 dependent instructions: ~100 clk per MMA, which starved the tensor pipe.)  Two warps because
-            // tcgen05.mma issue blocks while the pipe's queue is full: one warp doing both could not keep up with
-            // the softmax warpgroups.  Q.K^T (n + 3) reuses the S buffer whose P feeds P.V (n): the Q.K^T warp waits
-            // for the COMPLETION of P.V (n) (s_free), since MMAs of different threads are not ordered.
-            const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
-            const uint32_t sQ_u = __shfl_sync(0xffffffffu, ptx::smem_u32(sQ), 0);
-            const uint32_t sKV_u = __shfl_sync(0xffffffffu, ptx::smem_u32(sKV), 0);
-
-            // cursor over the CTA's sequence of tile-steps (item, tile t, key tile j)
-            int it = blockIdx.x, k = 0, nsteps = 0, qi = 0;
-            uint32_t n = 0;
-            Item I;
+        } else if (warp == 10) {
+            // ===================== S_t = Q.K^T issuer =====================
+            const uint32_t idesc_qk_full = ptx::make_idesc_bf16(QT, KT, 0, 0);
+            const uint32_t idesc_qk_last = ptx::make_idesc_bf16(QT, sh.last_n16, 0, 0);
             Ring ring;
-            auto seek = [&]() {  // position on the first live item at or after `it`
-                while (it < sh.n_items) {
-                    I = decode_item(sh, it);
-                    if (I.nt) break;
-                    it += gridDim.x;
-                }
-                k = 0;
-                nsteps = it < sh.n_items ? I.nt * nkv : 0;
-            };
-            auto advance = [&]() {
-                ++n;
-                if (++k == nsteps) {
-                    it += gridDim.x;
-                    ++qi;
-                    seek();
-                }
-            };
-            seek();
-
-            if (warp == 10) {
-                const uint32_t idesc_qk_full = ptx::make_idesc_bf16(QT, KT, 0, 0);
-                const uint32_t idesc_qk_last = ptx::make_idesc_bf16(QT, sh.last_n16, 0, 0);
-                while (it < sh.n_items) {
-                    const int t = I.nt == 2 ? (k & 1) : 0, j = I.nt == 2 ? (k >> 1) : k;
-                    const int qs = qi & 1;
-                    const uint32_t buf = n % NSBUF, use = n / NSBUF;
-                    if (k == 0) ptx::mbar_wait(&q_full[qs], (qi >> 1) & 1);
-                    if (!(I.same && t == 1)) {  // first user of a K/V slot
-                        ring.next();
-                        ptx::mbar_wait(&kv_full[ring.slot], ring.ph);
-                    }
-                    const uint64_t qdesc = ptx::make_smem_desc_sw128(sQ_u + (qs * 2 + t) * TILE_BYTES, 1024);
-                    const uint64_t kdesc = ptx::make_smem_desc_sw128(sKV_u + ring.slot * 2 * TILE_BYTES, 1024);
-                    const uint32_t d = tb + buf * 128;
-                    const uint32_t idesc = j == nkv - 1 ? idesc_qk_last : idesc_qk_full;
-                    const bool item_done = k == nsteps - 1;
-                    TRACE(14, n);
-                    if (use > 0) ptx::mbar_wait(&s_free[buf], (use - 1) & 1);  // P.V (n - 3) has consumed the buffer
-                    ptx::tc_fence_after();
-                    TRACE(15, n);
-                    if (ptx::elect_one()) {
-#pragma unroll
-                        for (int kk = 0; kk < HD / 16; ++kk)
-                            ptx::mma_bf16_ss(d, qdesc + 2 * kk, kdesc + 2 * kk, idesc, kk != 0);
-                        ptx::mma_commit(&s_full[buf]);
-                        if (item_done) ptx::mma_commit(&q_empty[qs]);  // all Q.K^T of the item issued: its Q tiles are free
-                    }
-                    __syncwarp();
-                    TRACE(10, n);
-                    advance();
-                }
-            } else {
-                constexpr uint32_t idesc_pv = ptx::make_idesc_bf16(QT, HD, 0, 1);  // A = P (TMEM), B = V MN-major
-                const int ksteps_last = sh.last_n16 / 16;
-                uint32_t o_uses[2] = {0, 0};  // items that have used O_t so far
-                while (it < sh.n_items) {
-                    const int t = I.nt == 2 ? (k & 1) : 0, j = I.nt == 2 ? (k >> 1) : k;
-                    if (!(I.same && t == 1)) ring.next();
-                    const uint32_t buf = n % NSBUF;
-                    // V tile: rows = keys (K dim), 128 bytes of head-dim per row (N contiguous) -> MN-major; 8-key groups
-                    // are 1024 bytes apart; one UMMA_K step (16 keys) = 2048 bytes.  P: 16 bf16 = 8 TMEM columns per step.
-                    const uint64_t vdesc =
-                        ptx::make_smem_desc_sw128(sKV_u + ring.slot * 2 * TILE_BYTES + TILE_BYTES, 1024, 1024);
-                    const bool last_tile = j == nkv - 1;
-                    uint64_t* kv_bar = !(I.same && t == 0) ? &kv_empty[ring.slot] : nullptr;  // last user of the slot
-                    const uint32_t d_o = tb + O_COL + t * 64, a_p = tb + buf * 128;
-                    const uint32_t acc0 = j != 0;
-                    if (j == 0) {  // O_t is rewritten: the previous item's epilogue must have drained it
-                        ptx::mbar_wait(&o_empty[t], (o_uses[t] & 1) ^ 1);
-                        ++o_uses[t];
-                    }
-                    TRACE(11, n);
-                    ptx::mbar_wait(&p_full[buf], (n / NSBUF) & 1);
-                    ptx::tc_fence_after();
-                    TRACE(12, n);
-                    if (ptx::elect_one()) {
-                        if (!last_tile) {
-                            ptx::mma_bf16_ts(d_o, a_p, vdesc, idesc_pv, acc0);
-#pragma unroll
-                            for (int kk = 1; kk < KT / 16; ++kk)
-                                ptx::mma_bf16_ts(d_o, a_p + kk * 8, vdesc + kk * (2048 >> 4), idesc_pv, 1);
-                        } else {
-                            ptx::mma_bf16_ts(d_o, a_p, vdesc, idesc_pv, acc0);
-                            for (int kk = 1; kk < ksteps_last; ++kk)
-                                ptx::mma_bf16_ts(d_o, a_p + kk * 8, vdesc + kk * (2048 >> 4), idesc_pv, 1);
+            int qi = 0;
+            uint32_t cnt[2] = {0, 0};  // tile-steps issued so far per tile slot
+            for (; !w.done(sh); w.next(sh)) {
+                const Item I = w.get(sh);
+                if (I.nt == 0) continue;
+                const int qs = qi & 1;
+                ptx::mbar_wait(&q_full[qs], (qi >> 1) & 1);
+                for (int j = 0; j < nkv; ++j) {
+                    for (int t = 0; t < I.nt; ++t) {
+                        if (!(I.same && t == 1)) {  // first user of a K/V slot
+                            ring.next();
+                            ptx::mbar_wait(&kv_full[ring.slot], ring.ph);
                         }
-                        ptx::mma_commit(&s_free[buf]);
-                        ptx::mma_commit(&o_full[t]);
-                        if (kv_bar) ptx::mma_commit(kv_bar);
+                        const uint64_t qdesc = ptx::make_smem_desc_sw128(sQ_u + (qs * 2 + t) * TILE_BYTES, 1024);
+                        const uint64_t kdesc = ptx::make_smem_desc_sw128(sKV_u + ring.slot * 2 * TILE_BYTES, 1024);
+                        const uint32_t d = tb + S_COL + t * 128;
+                        const uint32_t idesc = j == nkv - 1 ? idesc_qk_last : idesc_qk_full;
+                        const bool item_done = j == nkv - 1 && t == I.nt - 1;
+                        const uint32_t c = cnt[t]++;
+                        TRACE(14, c);
+                        if (c > 0) ptx::mbar_wait(&s_free[t], (c - 1) & 1);  // the previous S_t sits in registers
+                        ptx::tc_fence_after();
+                        TRACE(15, c);
+                        if (ptx::elect_one()) {
+#pragma unroll
+                            for (int kk = 0; kk < HD / 16; ++kk)
+                                ptx::mma_bf16_ss(d, qdesc + 2 * kk, kdesc + 2 * kk, idesc, kk != 0);
+                            ptx::mma_commit(&s_full[t]);
+                            if (item_done) ptx::mma_commit(&q_empty[qs]);  // all Q.K^T of the item issued: Q tiles are free
+                        }
+                        __syncwarp();
+                        TRACE(10, c);
                     }
-                    __syncwarp();
-                    TRACE(13, n);
-                    advance();
+                }
+                ++qi;
+            }
+        } else if (warp == 9) {
+            // ===================== O_t += P_t.V issuer =====================
+            constexpr uint32_t idesc_pv = ptx::make_idesc_bf16(QT, HD, 0, 1);  // A = P (TMEM), B = V MN-major
+            const int ksteps_last = sh.last_n16 / 16;
+            Ring ring;
+            uint32_t cnt[2] = {0, 0};     // tile-steps issued so far per tile slot
+            uint32_t o_uses[2] = {0, 0};  // items that have used O_t so far
+            for (; !w.done(sh); w.next(sh)) {
+                const Item I = w.get(sh);
+                if (I.nt == 0) continue;
+                for (int j = 0; j < nkv; ++j) {
+                    for (int t = 0; t < I.nt; ++t) {
+                        if (!(I.same && t == 1)) ring.next();
+                        // V tile: rows = keys (K dim), 128 bytes of head-dim per row (N contiguous) -> MN-major; 8-key
+                        // groups are 1024 bytes apart; one UMMA_K step (16 keys) = 2048 bytes.  P: 16 bf16 = 8 TMEM columns.
+                        const uint64_t vdesc =
+                            ptx::make_smem_desc_sw128(sKV_u + ring.slot * 2 * TILE_BYTES + TILE_BYTES, 1024, 1024);
+                        const bool last_tile = j == nkv - 1;
+                        uint64_t* kv_bar = !(I.same && t == 0) ? &kv_empty[ring.slot] : nullptr;  // last user of the slot
+                        const uint32_t d_o = tb + O_COL + t * 64, a_p = tb + P_COL + t * 64;
+                        const uint32_t acc0 = j != 0;
+                        if (j == 0) {  // O_t is rewritten: the previous item's epilogue must have drained it
+                            ptx::mbar_wait(&o_empty[t], (o_uses[t] & 1) ^ 1);
+                            ++o_uses[t];
+                        }
+                        const uint32_t c = cnt[t]++;
+                        TRACE(11, c);
+                        ptx::mbar_wait(&p_full[t], c & 1);
+                        ptx::tc_fence_after();
+                        TRACE(12, c);
+                        if (ptx::elect_one()) {
+                            if (!last_tile) {
+                                ptx::mma_bf16_ts(d_o, a_p, vdesc, idesc_pv, acc0);
+#pragma unroll
+                                for (int kk = 1; kk < KT / 16; ++kk)
+                                    ptx::mma_bf16_ts(d_o, a_p + kk * 8, vdesc + kk * (2048 >> 4), idesc_pv, 1);
+                            } else {
+                                ptx::mma_bf16_ts(d_o, a_p, vdesc, idesc_pv, acc0);
+                                for (int kk = 1; kk < ksteps_last; ++kk)
+                                    ptx::mma_bf16_ts(d_o, a_p + kk * 8, vdesc + kk * (2048 >> 4), idesc_pv, 1);
+                            }
+                            ptx::mma_commit(&o_full[t]);
+                            if (kv_bar) ptx::mma_commit(kv_bar);
+                        }
+                        __syncwarp();
+                        TRACE(13, c);
+                    }
                 }
             }
         }
@@ -415,91 +461,116 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict
         const int t = warp >> 2;  // tile slot handled by this warpgroup
         const int wq = warp & 3;
         const uint32_t lane_base = uint32_t(wq * 32) << 16;
+        const uint32_t s_addr = tmem_base + lane_base + S_COL + t * 128;
+        const uint32_t p_addr = tmem_base + lane_base + P_COL + t * 64;
         const uint32_t o_addr = tmem_base + lane_base + O_COL + t * 64;
         const int nch_last = (sh.last_n16 + 31) >> 5;  // 32-key chunks of the ragged last key tile that P.V reads
-        uint32_t n_base = 0;   // tile-steps issued before the current item
-        uint32_t steps = 0;    // tile-steps of slot t completed so far (o_full phase counter)
+        uint32_t steps = 0;    // tile-steps of slot t completed so far (phase counter of s_full / o_full)
 
-        for (int it = blockIdx.x; it < sh.n_items; it += gridDim.x) {
+        // The O epilogue of an item is DEFERRED until this warpgroup has pushed the first key tile of its next item
+        // through the softmax: the O -> global stores then sit under the MMAs / exp2 of the neighbouring work instead
+        // of leaving the MUFU pipe idle at every item boundary.
+        struct Pending {
+            bool any = false, live = false, row_ok = false;
+            uint32_t parity = 0;
+            float inv_l = 0.f;
+            bf16* dst = nullptr;
+        } pend;
+        auto flush_epilogue = [&]() {  // O / l -> bf16 rows of the pending item
+            ptx::mbar_wait(&o_full[t], pend.parity);  // the item's last P.V has landed
+            ptx::tc_fence_after();
+            TRACE(4, 0);
+            if (pend.live) {
+                uint32_t v[2][32];
+                ptx::tmem_ld_32x32(o_addr, v[0]);
+                ptx::tmem_ld_32x32(o_addr + 32, v[1]);
+                ptx::tmem_ld_wait();
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&o_empty[t]);  // O_t may be overwritten by the next item
+                if (pend.row_ok) {
+                    const float inv = pend.inv_l;
+#pragma unroll
+                    for (int c = 0; c < 2; ++c)
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            uint4 pk;
+                            pk.x = pack_bf16(__uint_as_float(v[c][8 * q + 0]) * inv, __uint_as_float(v[c][8 * q + 1]) * inv);
+                            pk.y = pack_bf16(__uint_as_float(v[c][8 * q + 2]) * inv, __uint_as_float(v[c][8 * q + 3]) * inv);
+                            pk.z = pack_bf16(__uint_as_float(v[c][8 * q + 4]) * inv, __uint_as_float(v[c][8 * q + 5]) * inv);
+                            pk.w = pack_bf16(__uint_as_float(v[c][8 * q + 6]) * inv, __uint_as_float(v[c][8 * q + 7]) * inv);
+                            reinterpret_cast<uint4*>(pend.dst + c * 32)[q] = pk;
+                        }
+                }
+            } else {
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&o_empty[t]);
+            }
+            pend.any = false;
+            TRACE(5, 0);
+        };
+
+        ItemWalk w;
+        for (w.init(sh); !w.done(sh); w.next(sh)) {
             int nt, q0, h, b;
             {
-                const Item I = decode_item(sh, it);
+                const Item I = w.get(sh);
                 nt = I.nt; q0 = (t ? I.qB : I.qA) * QT; h = t ? I.hB : I.hA; b = I.b;
             }
             if (nt == 0) continue;
             if (t < nt) {
                 const bool live = q0 + wq * 32 < sh.L;  // does this warp own any real query row?
                 float m_ref = 0.f, l = 0.f;
-                const uint32_t n0 = n_base + (nt == 2 ? t : 0), dn = nt == 2 ? 2 : 1;
                 for (int j = 0; j < nkv; ++j) {
-                    const uint32_t n = n0 + j * dn;
-                    const uint32_t buf = n % NSBUF;
-                    const uint32_t s_addr = tmem_base + lane_base + buf * 128;
-                    TRACE(0, n);
-                    ptx::mbar_wait(&s_full[buf], (n / NSBUF) & 1);
+                    TRACE(0, steps);
+                    ptx::mbar_wait(&s_full[t], steps & 1);
                     ptx::tc_fence_after();
-                    TRACE(1, n);
+                    TRACE(1, steps);
+                    // before P_t is rewritten / O_t rescaled, the previous P.V of this slot must be complete: the previous
+                    // key tile's (j > 0) or the previous item's last one (same phase the deferred epilogue waits for)
+                    const bool wait_prev = j > 0 || pend.any;
+                    uint64_t* of = &o_full[t];
+                    const uint32_t ofp = (steps - 1) & 1;
                     if (live) {
-                        uint64_t* of = &o_full[t];
-                        const uint32_t ofp = (steps - 1) & 1;
                         if (j < nkv - 1) {
-                            softmax_tile<4, false>(s_addr, o_addr, KT, j == 0, m_ref, l, of, ofp);
+                            softmax_tile<4, false>(s_addr, p_addr, o_addr, KT, j == 0, wait_prev, m_ref, l, &s_free[t], of, ofp, lane);
                         } else {
+                            const int nv = sh.last_valid;
                             switch (nch_last) {
-                                case 1: softmax_tile<1, true>(s_addr, o_addr, sh.last_valid, j == 0, m_ref, l, of, ofp); break;
-                                case 2: softmax_tile<2, true>(s_addr, o_addr, sh.last_valid, j == 0, m_ref, l, of, ofp); break;
-                                case 3: softmax_tile<3, true>(s_addr, o_addr, sh.last_valid, j == 0, m_ref, l, of, ofp); break;
-                                default: softmax_tile<4, true>(s_addr, o_addr, sh.last_valid, j == 0, m_ref, l, of, ofp); break;
+                                case 1: softmax_tile<1, true>(s_addr, p_addr, o_addr, nv, j == 0, wait_prev, m_ref, l, &s_free[t], of, ofp, lane); break;
+                                case 2: softmax_tile<2, true>(s_addr, p_addr, o_addr, nv, j == 0, wait_prev, m_ref, l, &s_free[t], of, ofp, lane); break;
+                                case 3: softmax_tile<3, true>(s_addr, p_addr, o_addr, nv, j == 0, wait_prev, m_ref, l, &s_free[t], of, ofp, lane); break;
+                                default: softmax_tile<4, true>(s_addr, p_addr, o_addr, nv, j == 0, wait_prev, m_ref, l, &s_free[t], of, ofp, lane); break;
                             }
                         }
-                        TRACE(2, n);
+                        TRACE(2, steps);
                         ptx::tmem_st_wait();
-                    } else if (j > 0) {
-                        ptx::mbar_wait(&o_full[t], (steps - 1) & 1);  // keep in step with o_full (see softmax_tile)
+                    } else {
+                        if (lane == 0) ptx::mbar_arrive(&s_free[t]);
+                        if (wait_prev) ptx::mbar_wait(of, ofp);  // keep in step with o_full
                     }
                     ptx::tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive(&p_full[buf]);
-                    TRACE(3, n);
+                    if (lane == 0) ptx::mbar_arrive(&p_full[t]);
+                    TRACE(3, steps);
                     ++steps;
+                    // the previous item's epilogue, now that this item's first P is on its way (P.V of j = 0 waits for
+                    // o_empty, i.e. for the O loads of the epilogue)
+                    if (j == 0 && pend.any) flush_epilogue();
                 }
-                // epilogue: O / l -> bf16 rows
-                ptx::mbar_wait(&o_full[t], (steps - 1) & 1);
-                ptx::tc_fence_after();
-                TRACE(4, n0);
-                if (live) {
-                    const int qi = q0 + wq * 32 + lane;
-                    const float inv = 1.f / l;
-                    bf16* dst = out + ((long long)b * sh.L + qi) * D + h * HD;
-                    uint32_t v[2][32];
-                    ptx::tmem_ld_32x32(o_addr, v[0]);
-                    ptx::tmem_ld_32x32(o_addr + 32, v[1]);
-                    ptx::tmem_ld_wait();
-                    ptx::tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive(&o_empty[t]);  // O_t may be overwritten by the next item
-                    if (qi < sh.L) {
-#pragma unroll
-                        for (int c = 0; c < 2; ++c)
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                uint4 pk;
-                                pk.x = pack_bf16(__uint_as_float(v[c][8 * q + 0]) * inv, __uint_as_float(v[c][8 * q + 1]) * inv);
-                                pk.y = pack_bf16(__uint_as_float(v[c][8 * q + 2]) * inv, __uint_as_float(v[c][8 * q + 3]) * inv);
-                                pk.z = pack_bf16(__uint_as_float(v[c][8 * q + 4]) * inv, __uint_as_float(v[c][8 * q + 5]) * inv);
-                                pk.w = pack_bf16(__uint_as_float(v[c][8 * q + 6]) * inv, __uint_as_float(v[c][8 * q + 7]) * inv);
-                                reinterpret_cast<uint4*>(dst + c * 32)[q] = pk;
-                            }
-                    }
-                } else {
-                    ptx::tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive(&o_empty[t]);
-                }
-                TRACE(5, n0);
+                const int qi = q0 + wq * 32 + lane;
+                pend.any = true;
+                pend.live = live;
+                pend.row_ok = qi < sh.L;
+                pend.parity = (steps - 1) & 1;
+                pend.inv_l = 1.f / l;
+                pend.dst = out + ((long long)b * sh.L + qi) * D + h * HD;
+            } else if (pend.any) {
+                flush_epilogue();  // this tile slot sits the item out (odd head count)
             }
-            n_base += nt * nkv;
         }
+        if (pend.any) flush_epilogue();
     }
 
     ptx::tc_fence_before();

@@ -843,7 +843,8 @@ int pdm_debug_linear(const float* A, const float* A2, const float* W, const floa
         cudaStream_t s = (cudaStream_t)stream;
         const int Kt = K + (A2 ? K2 : 0);
         GemmProblem g;
-        g.K1 = K; g.K2 = A2 ? K2 : 0; g.N = N; g.nb = 1; g.Lr = M; g.bias = bias; g.gelu = gelu != 0;
+        g.K1 = K; g.K2 = A2 ? K2 : 0; g.N = N; g.nb = 1; g.Lr = M; g.bias = bias; g.gelu = (gelu & 1) != 0;
+        const bool out16 = (gelu & 2) != 0 && precision == PDM_PREC_BF16 && !resid;  // bf16-only output (qkv / fc1 form)
         g.out32 = out;
         if (resid) {  // the production kernels update the fp32 residual stream in place
             PDM_CHECK_CUDA(cudaMemcpyAsync(out, resid, (size_t)M * N * sizeof(float), cudaMemcpyDeviceToDevice, s));
@@ -859,10 +860,20 @@ int pdm_debug_linear(const float* A, const float* A2, const float* W, const floa
             if (A2) convert_f32_bf16(A2, (bf16*)a216.p, (long long)M * K2, s);
             convert_f32_bf16(W, (bf16*)w16.p, (long long)N * Kt, s);
             g.A1 = a16.p; g.A2 = A2 ? a216.p : nullptr; g.W16 = (const bf16*)w16.p;
+            DevBuf o16(out16 ? (size_t)M * N * 2 : 0);
+            if (out16) {
+                g.out32 = nullptr;
+                g.out2 = o16.p;
+            }
             gemm_tc_bf16(g, s);
             // timing re-runs the identical launch; with a residual the output keeps accumulating, so
             // callers time without `resid` aliasing `out` (resid given -> extra launches use out as scratch)
             time_kernel([&] { gemm_tc_bf16(g, s); }, iters, ms, s);
+            if (out16) {
+                bf16_to_f32_kernel<<<(unsigned)ceil_div_ll((long long)M * N, 256), 256, 0, s>>>((const bf16*)o16.p, out,
+                                                                                               (long long)M * N);
+                check_launch("bf16_to_f32");
+            }
             PDM_CHECK_CUDA(cudaStreamSynchronize(s));
         }
     });

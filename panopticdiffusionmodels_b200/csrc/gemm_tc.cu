@@ -175,8 +175,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
+        // ===================== TMA producer (whole warp walks the schedule, one elected lane issues) =====================
+        {
+            const uint32_t smem_u = __shfl_sync(0xffffffffu, ptx::smem_u32(smem), 0);
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = unit_id; tile < p.total_tiles; tile += n_units) {
@@ -190,18 +191,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
                 const int n0 = nt * BN + (int)rank * (BN / NCTA);
                 for (int kb = 0; kb < p.KB; ++kb) {
                     ptx::mbar_wait(&empty[stage], phase ^ 1);
-                    uint8_t* sa = smem + stage * STAGE_BYTES;
-                    uint8_t* sb = sa + A_BYTES;
-                    if (rank == 0) ptx::mbar_expect_tx(&full[stage], NCTA * STAGE_BYTES);
+                    const uint32_t sa = smem_u + stage * STAGE_BYTES;
+                    const uint32_t sb = sa + A_BYTES;
                     const CUtensorMap* ta = kb < p.KB1 ? &tmA1 : &tmA2;
                     const int ka = (kb < p.KB1 ? kb : kb - p.KB1) * BK;
-                    if (NCTA == 2) {
-                        ptx::tma_load_3d_2sm(ta, &full[stage], sa, ka, t0, b);
-                        ptx::tma_load_3d_2sm(&tmB, &full[stage], sb, kb * BK, n0, 0);
-                    } else {
-                        ptx::tma_load_3d(ta, &full[stage], sa, ka, t0, b);
-                        ptx::tma_load_3d(&tmB, &full[stage], sb, kb * BK, n0, 0);
+                    if (ptx::elect_one()) {
+                        if (rank == 0) ptx::mbar_expect_tx(&full[stage], NCTA * STAGE_BYTES);
+                        if (NCTA == 2) {
+                            ptx::tma_load_3d_2sm(ta, &full[stage], sa, ka, t0, b);
+                            ptx::tma_load_3d_2sm(&tmB, &full[stage], sb, kb * BK, n0, 0);
+                        } else {
+                            ptx::tma_load_3d(ta, &full[stage], sa, ka, t0, b);
+                            ptx::tma_load_3d(&tmB, &full[stage], sb, kb * BK, n0, 0);
+                        }
                     }
+                    __syncwarp();
                     if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1;
@@ -210,9 +214,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer (leader CTA, one thread) =====================
-        if (rank == 0 && lane == 0) {
+        // ===================== MMA issuer (leader CTA) =====================
+        // The whole warp runs the loop (warp-uniform operands -> uniform registers); one elected lane issues the
+        // tcgen05.mma / commit instructions.  A single-lane region made the compiler wrap every MMA in a
+        // uniformisation loop of ~17 dependent instructions (~100 clk per MMA: issue-bound at K = 512).
+        if (rank == 0) {
             constexpr uint32_t idesc = ptx::make_idesc_bf16(NCTA * BM, BN);
+            const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+            const uint32_t smem_u = __shfl_sync(0xffffffffu, ptx::smem_u32(smem), 0);
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
@@ -221,26 +230,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
                 const uint32_t aphase = (it >> 1) & 1;
                 ptx::mbar_wait(&tempty[as], aphase ^ 1);
                 ptx::tc_fence_after();
-                const uint32_t d_tmem = tmem_base + as * BN;
+                const uint32_t d_tmem = tb + as * BN;
                 for (int kb = 0; kb < p.KB; ++kb) {
                     ptx::mbar_wait(&full[stage], phase);
                     ptx::tc_fence_after();
-                    const uint32_t sa = ptx::smem_u32(smem + stage * STAGE_BYTES);
+                    const uint32_t sa = smem_u + stage * STAGE_BYTES;
                     const uint64_t adesc = ptx::make_smem_desc_sw128(sa, 1024);
                     const uint64_t bdesc = ptx::make_smem_desc_sw128(sa + A_BYTES, 1024);
+                    if (ptx::elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle row
-                        if (NCTA == 2) ptx::mma_bf16_ss_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-                        else ptx::mma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                        for (int k = 0; k < BK / 16; ++k) {
+                            // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle row
+                            if (NCTA == 2) ptx::mma_bf16_ss_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                            else ptx::mma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                        }
+                        if (NCTA == 2) ptx::mma_commit_2sm(&empty[stage], 3); else ptx::mma_commit(&empty[stage]);
+                        if (kb == p.KB - 1) {
+                            if (NCTA == 2) ptx::mma_commit_2sm(&tfull[as], 3); else ptx::mma_commit(&tfull[as]);
+                        }
                     }
-                    if (NCTA == 2) ptx::mma_commit_2sm(&empty[stage], 3); else ptx::mma_commit(&empty[stage]);
+                    __syncwarp();
                     if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1;
                     }
                 }
-                if (NCTA == 2) ptx::mma_commit_2sm(&tfull[as], 3); else ptx::mma_commit(&tfull[as]);
             }
         }
     } else {

@@ -62,9 +62,9 @@ def main():
 
     only = set(a.only.split(",")) if a.only else {"gemm", "layernorm", "attention"}
     if "gemm" in only:
-        gemm("gemm_qkv", 3 * D, D)
+        gemm("gemm_qkv(bf16 out)", 3 * D, D, gelu=2)
         gemm("gemm_proj(+resid)", D, D, resid=True)
-        gemm("gemm_fc1(+gelu)", 4 * D, D, gelu=1)
+        gemm("gemm_fc1(+gelu, bf16 out)", 4 * D, D, gelu=3)
         gemm("gemm_fc2(+resid)", D, 4 * D, resid=True)
         gemm("gemm_skip", D, D, K2=D)
 
