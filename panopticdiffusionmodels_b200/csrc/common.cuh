@@ -67,6 +67,8 @@ struct GemmProblem {
     int resid_bs = 0;
     float* out32 = nullptr;
     int out32_bs = 0;
+    float* out32b = nullptr;  // optional second copy of out32 (tcgen05 kernel only)
+    int out32b_bs = 0;
     void* out2 = nullptr;
     int out2_bs = 0;
     bool gelu = false;

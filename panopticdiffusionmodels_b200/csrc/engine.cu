@@ -454,14 +454,18 @@ struct pdm_engine {
     }
 
     // x += zero_conv(mx_act[:, :L1])  (libs/uvit_t2i.py:432-436); also emits the activation copy of x
+    // also_mx: additionally store the updated x rows into mx[:, :L1] -- the concat of the next layer, fused (bf16 mode)
     void run_zero_conv(const LinearW& z, Workspace& ws, const void* mx_act, void* out2, int nb, int prec,
-                       cudaStream_t s) {
+                       cudaStream_t s, bool also_mx = false) {
         Scope sc(this, "gemm_zeroconv", s);
         GemmProblem g;
         g.A1 = mx_act; g.K1 = D; g.a1_bs = L2;
         g.W32 = z.w32; g.W16 = z.w16; g.bias = z.b; g.N = D;
         g.nb = nb; g.Lr = L1;
         g.resid = ws.x; g.resid_bs = L1; g.out32 = ws.x; g.out32_bs = L1; g.out2 = out2; g.out2_bs = L1;
+        if (also_mx) {
+            g.out32b = ws.mx; g.out32b_bs = L2;
+        }
         gemm(g, prec, s);
     }
 
@@ -510,33 +514,36 @@ struct pdm_engine {
             for (int j = 0; j < half; ++j)
                 run_block(out_b[j], ws, ws.x, nb, Lx, ws.xb, ws.skipx[half - 1 - j], j + 1 < half ? ws.xb : nullptr, prec, s);
         } else {
+            // mx[:, :L1] = x before every layer pair (libs/uvit_t2i.py two-stream forward).  In bf16 mode only the first
+            // copy is a kernel: the zero-conv GEMM that finishes a layer stores its x rows into mx as well.
+            const bool fuse = b16;
             int li = 0;
             for (int i = 0; i < half; ++i, ++li) {
-                {
+                if (!fuse || li == 0) {
                     Scope sc(this, "concat", s);
                     copy_rows(ws.mx, L2, ws.x, L1, L1, nb, D * 4, s);
                 }
                 run_block(in_b[i], ws, ws.x, nb, L1, nullptr, nullptr, nullptr, prec, s);
                 run_block(in_bm[i], ws, ws.mx, nb, L2, nullptr, nullptr, ws.skipm[i], prec, s);
-                run_zero_conv(zc[li], ws, ws.skipm[i], ws.skipx[i], nb, prec, s);
+                run_zero_conv(zc[li], ws, ws.skipm[i], ws.skipx[i], nb, prec, s, fuse);
             }
-            {
+            if (!fuse) {
                 Scope sc(this, "concat", s);
                 copy_rows(ws.mx, L2, ws.x, L1, L1, nb, D * 4, s);
             }
             run_block(mid_b, ws, ws.x, nb, L1, nullptr, nullptr, nullptr, prec, s);
             run_block(mid_bm, ws, ws.mx, nb, L2, nullptr, nullptr, ws.mxb, prec, s);
-            run_zero_conv(zc[li], ws, ws.mxb, ws.xb, nb, prec, s);
+            run_zero_conv(zc[li], ws, ws.mxb, ws.xb, nb, prec, s, fuse);
             ++li;
             for (int j = 0; j < half; ++j, ++li) {
                 {
                     Scope sc(this, "concat", s);
-                    copy_rows(ws.mx, L2, ws.x, L1, L1, nb, D * 4, s);
+                    if (!fuse) copy_rows(ws.mx, L2, ws.x, L1, L1, nb, D * 4, s);
                     copy_rows(ws.mxb, L2, ws.xb, L1, L1, nb, (int)(D * actsz), s);
                 }
                 run_block(out_b[j], ws, ws.x, nb, L1, ws.xb, ws.skipx[half - 1 - j], nullptr, prec, s);
                 run_block(out_bm[j], ws, ws.mx, nb, L2, ws.mxb, ws.skipm[half - 1 - j], ws.mxb, prec, s);
-                run_zero_conv(zc[li], ws, ws.mxb, ws.xb, nb, prec, s);
+                run_zero_conv(zc[li], ws, ws.mxb, ws.xb, nb, prec, s, fuse && j + 1 < half);
             }
         }
         {

@@ -32,11 +32,16 @@ namespace {
 
 constexpr int BM = 128;  // accumulator rows per CTA
 constexpr int BN = 256, BK = 64;
-constexpr int EPI_WARPS = 8;
+#ifndef PDM_GEMM_EPI_WARPS
+#define PDM_GEMM_EPI_WARPS 8
+#endif
+constexpr int EPI_WARPS = PDM_GEMM_EPI_WARPS;  // 8 or 16: each covers one TMEM lane quarter x (BN / (EPI_WARPS / 4)) columns
+constexpr int WCOLS = 256 / (EPI_WARPS / 4);   // accumulator columns per epilogue warp
+constexpr int NBLK = WCOLS / 32;               // 32-column blocks per epilogue warp
 constexpr int THREADS = 64 + EPI_WARPS * 32;
 constexpr int A_BYTES = BM * BK * 2;
 constexpr int SCR_STRIDE = 36;  // 32-bit words per scratch row: 128 B payload + 16 B pad (16 B aligned, conflict-free)
-constexpr int SCR_WORDS = 32 * SCR_STRIDE + 128;  // + 128 floats: this warp's slice of the bias vector
+constexpr int SCR_WORDS = 32 * SCR_STRIDE + WCOLS;  // + this warp's slice of the bias vector
 constexpr int SCR_BYTES = SCR_WORDS * 4;
 constexpr uint32_t TMEM_COLS = 512;
 
@@ -44,7 +49,7 @@ template <int NCTA>
 struct Cfg {
     static constexpr int B_BYTES = (BN / NCTA) * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = NCTA == 2 ? 5 : 3;
+    static constexpr int STAGES = NCTA == 2 ? (EPI_WARPS > 8 ? 4 : 5) : 3;
     static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + EPI_WARPS * SCR_BYTES + 256;
 };
 
@@ -56,6 +61,8 @@ struct TcParams {
     const float* bias;
     float* out32;     // fp32 output (nullptr: none)
     long long out32_bs;
+    float* out32b;    // optional second copy of the fp32 output (two-stream concat fused into the zero-conv)
+    long long out32b_bs;
     int accumulate;   // out32 += (residual stream update in place)
     bf16* out2;       // bf16 output (nullptr: none)
     long long out2_bs;
@@ -261,7 +268,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         // ===================== epilogue (own 128 rows) =====================
         const int ew = warp - 2;
         const int q = warp & 3;    // TMEM lane quarter this warp may access
-        const int half = ew >> 2;  // which 128-column half of the tile
+        const int half = ew >> 2;  // which WCOLS-column slice of the tile
         uint32_t* scr = reinterpret_cast<uint32_t*>(scr_base + ew * SCR_BYTES);
         float* sbias = reinterpret_cast<float*>(scr + 32 * SCR_STRIDE);  // [128]
         const bool packed = (p.out32 == nullptr) && ((p.N & 7) == 0);
@@ -277,13 +284,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
             const int trow0 = t0 + q * 32;
-            const int ncol0 = nt * BN + half * 128;  // first column of this warp's slice
-            const uint32_t tbase = tmem_base + (uint32_t(q * 32) << 16) + as * BN + half * 128;
+            const int ncol0 = nt * BN + half * WCOLS;  // first column of this warp's slice
+            const uint32_t tbase = tmem_base + (uint32_t(q * 32) << 16) + as * BN + half * WCOLS;
             if (packed) {
                 // ---- bf16-only output: 2 chunks of 64 columns; bias/GELU in the row domain, pack, transpose ----
                 if (p.bias) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
+                    for (int i = 0; i < NBLK; ++i) {
                         const int c = ncol0 + lane + 32 * i;
                         sbias[lane + 32 * i] = c < p.N ? __ldg(p.bias + c) : 0.f;
                     }
@@ -291,52 +298,63 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
                 __syncwarp();
                 ptx::mbar_wait(&tfull[as], aphase);
                 ptx::tc_fence_after();
-#pragma unroll 1
-                for (int chunk = 0; chunk < 2; ++chunk) {
-                    uint32_t* srow = scr + lane * SCR_STRIDE;
+                // 4 blocks of 32 columns, software-pipelined: the TMEM load of block k+1 and the bias reads of block k are
+                // in flight while block k goes through bias / GELU / pack (the epilogue is latency-bound with 2 warps per
+                // scheduler: measured 44 % issue utilisation, "wait" + short-scoreboard stalls dominating)
+                uint32_t v[2][32];
+                ptx::tmem_ld_32x32(tbase, v[0]);
+                uint32_t* srow = scr + lane * SCR_STRIDE;
 #pragma unroll
-                    for (int hh = 0; hh < 2; ++hh) {
-                        uint32_t v[32];
-                        ptx::tmem_ld_32x32(tbase + chunk * 64 + hh * 32, v);
-                        ptx::tmem_ld_wait();
-                        if (chunk == 1 && hh == 1) release_accumulator<NCTA>(&tempty[as], rank, lane);
+                for (int blk = 0; blk < NBLK; ++blk) {
+                    const int chunk = blk >> 1, hh = blk & 1;
+                    float4 bv[8];
+                    if (p.bias) {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            float f[8];
+                        for (int i = 0; i < 8; ++i) bv[i] = *reinterpret_cast<const float4*>(sbias + blk * 32 + 4 * i);
+                    }
+                    ptx::tmem_ld_wait();
+                    if (blk < NBLK - 1) ptx::tmem_ld_32x32(tbase + (blk + 1) * 32, v[(blk + 1) & 1]);
+                    else release_accumulator<NCTA>(&tempty[as], rank, lane);
 #pragma unroll
-                            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[8 * j + e]);
-                            if (p.bias) {
-                                const float4 b0 = *reinterpret_cast<const float4*>(sbias + chunk * 64 + hh * 32 + 8 * j);
-                                const float4 b1 = *reinterpret_cast<const float4*>(sbias + chunk * 64 + hh * 32 + 8 * j + 4);
-                                f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-                                f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
-                            }
-                            if (p.gelu) {
+                    for (int j = 0; j < 4; ++j) {
+                        float f[8];
 #pragma unroll
-                                for (int e = 0; e < 8; e += 2) gelu_fast2(f[e], f[e + 1]);
-                            }
-                            *reinterpret_cast<uint4*>(srow + (hh * 4 + j) * 4) =
-                                make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
+                        for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[blk & 1][8 * j + e]);
+                        if (p.bias) {
+                            const float4 b0 = bv[2 * j], b1 = bv[2 * j + 1];
+                            f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+                            f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
                         }
-                    }
-                    __syncwarp();
-                    const int col = ncol0 + chunk * 64 + c8 * 8;
-                    bf16* orow = p.out2 + ((long long)b * p.out2_bs + trow0 + rsub) * p.N + col;
-                    const long long rstep = 4LL * p.N;
+                        if (p.gelu) {
 #pragma unroll
-                    for (int ps = 0; ps < 8; ++ps) {
-                        const int r = ps * 4 + rsub;
-                        const uint4 val = *reinterpret_cast<const uint4*>(scr + r * SCR_STRIDE + c8 * 4);
-                        if (col < p.N && trow0 + r < lr_eff) *reinterpret_cast<uint4*>(orow) = val;
-                        orow += rstep;
+                            for (int e = 0; e < 8; e += 2) gelu_fast2(f[e], f[e + 1]);
+                        }
+                        *reinterpret_cast<uint4*>(srow + (hh * 4 + j) * 4) =
+                            make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
                     }
-                    __syncwarp();
+                    if (hh == 1) {
+                        __syncwarp();
+                        const int col = ncol0 + chunk * 64 + c8 * 8;
+                        bf16* orow = p.out2 + ((long long)b * p.out2_bs + trow0 + rsub) * p.N + col;
+                        const long long rstep = 4LL * p.N;
+                        uint4 val[8];
+#pragma unroll
+                        for (int ps = 0; ps < 8; ++ps)
+                            val[ps] = *reinterpret_cast<const uint4*>(scr + (ps * 4 + rsub) * SCR_STRIDE + c8 * 4);
+#pragma unroll
+                        for (int ps = 0; ps < 8; ++ps) {
+                            if (col < p.N && trow0 + ps * 4 + rsub < lr_eff) *reinterpret_cast<uint4*>(orow) = val[ps];
+                            orow += rstep;
+                        }
+                        __syncwarp();
+                    }
                 }
             } else {
                 // ---- fp32 output (optionally += in place): 4 chunks of 32 columns through an fp32 transpose ----
                 const int colq = ncol0 + c8 * 4;  // this lane's 4 columns inside chunk 0
                 const long long rstep = 4LL * p.N;
                 float* o32 = p.out32 + ((long long)b * p.out32_bs + trow0 + rsub) * p.N + colq;
+                float* o32b = p.out32b ? p.out32b + ((long long)b * p.out32b_bs + trow0 + rsub) * p.N + colq : nullptr;
                 bf16* o16 = p.out2 ? p.out2 + ((long long)b * p.out2_bs + trow0 + rsub) * p.N + colq : nullptr;
                 float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);  // bias of the current chunk (next one is prefetched)
                 if (p.bias && colq < p.N) bb = __ldg(reinterpret_cast<const float4*>(p.bias + colq));
@@ -353,11 +371,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
                 ptx::mbar_wait(&tfull[as], aphase);
                 ptx::tc_fence_after();
 #pragma unroll 1
-                for (int chunk = 0; chunk < 4; ++chunk) {
+                for (int chunk = 0; chunk < NBLK; ++chunk) {
                     uint32_t v[32];
                     ptx::tmem_ld_32x32(tbase + chunk * 32, v);
                     ptx::tmem_ld_wait();
-                    if (chunk == 3) release_accumulator<NCTA>(&tempty[as], rank, lane);
+                    if (chunk == NBLK - 1) release_accumulator<NCTA>(&tempty[as], rank, lane);
                     uint32_t* srow = scr + lane * SCR_STRIDE;
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
@@ -365,10 +383,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
                     __syncwarp();
                     const int col = colq + 32 * chunk;
                     const bool col_ok = col < p.N;
-                    const bool next_ok = chunk < 3 && col + 32 < p.N;
+                    const bool next_ok = chunk < NBLK - 1 && col + 32 < p.N;
                     float4 bb_next = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (p.bias && next_ok) bb_next = __ldg(reinterpret_cast<const float4*>(p.bias + col + 32));
                     float* po = o32 + 32 * chunk;
+                    float* pob = o32b ? o32b + 32 * chunk : nullptr;
                     bf16* ph = o16 ? o16 + 32 * chunk : nullptr;
 #pragma unroll
                     for (int ps = 0; ps < 8; ++ps) {
@@ -386,9 +405,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
                         }
                         if (col_ok && row_ok) {
                             *reinterpret_cast<float4*>(po) = a;
+                            if (pob) *reinterpret_cast<float4*>(pob) = a;
                             if (ph) *reinterpret_cast<uint2*>(ph) = make_uint2(pack2(a.x, a.y), pack2(a.z, a.w));
                         }
                         po += rstep;
+                        if (pob) pob += rstep;
                         if (ph) ph += rstep;
                     }
                     bb = bb_next;
@@ -456,6 +477,8 @@ void launch(const GemmProblem& g, cudaStream_t s) {
     p.bias = g.bias;
     p.out32 = g.out32;
     p.out32_bs = g.out32_bs ? g.out32_bs : g.Lr;
+    p.out32b = g.out32b;
+    p.out32b_bs = g.out32b_bs ? g.out32b_bs : g.Lr;
     p.accumulate = g.resid != nullptr;
     p.out2 = (bf16*)g.out2;
     p.out2_bs = g.out2_bs ? g.out2_bs : g.Lr;
@@ -512,6 +535,7 @@ void gemm_tc_bf16(const GemmProblem& g, cudaStream_t s) {
     PDM_REQUIRE(g.N % 4 == 0, "gemm_tc: N must be a multiple of 4");
     PDM_REQUIRE(g.K1 % 8 == 0 && (!g.A2 || (g.K1 % BK == 0 && g.K2 % 8 == 0)), "gemm_tc: K alignment");
     PDM_REQUIRE(g.out32 || g.out2, "gemm_tc: no output");
+    PDM_REQUIRE(!g.out32b || g.out32, "gemm_tc: out32b needs out32");
     PDM_REQUIRE(!g.resid || (g.resid == g.out32 && (g.resid_bs ? g.resid_bs : g.Lr) == (g.out32_bs ? g.out32_bs : g.Lr)),
                 "gemm_tc: the residual must be the fp32 output (in-place accumulate)");
     static const bool one_cta = getenv("PDM_GEMM_1CTA") != nullptr;
