@@ -24,7 +24,6 @@ namespace pdm {
 
 CUtensorMap make_tmap_bf16_3d(const void* ptr, long long K, long long rows, long long nbatch, long long bs,
                               int box_rows, int box_k);
-void attention_tc_v1(const bf16* qkv, bf16* out, int nb, int L, int H, cudaStream_t s);
 void attention_tc3(const bf16* qkv, bf16* out, int nb, int L, int H, cudaStream_t s);
 
 namespace {
@@ -369,8 +368,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict
 }  // namespace
 
 void attention_tc_bf16(const bf16* qkv, bf16* out, int nb, int L, int H, cudaStream_t s) {
-    static const bool v1 = getenv("PDM_ATTN_V1") != nullptr;
-    if (v1) return attention_tc_v1(qkv, out, nb, L, H, s);
+    // production kernel: attention_tc3.cu; this file's non-persistent predecessor stays selectable for A/B timing
     static const bool v2 = getenv("PDM_ATTN_V2") != nullptr;
     if (!v2) return attention_tc3(qkv, out, nb, L, H, s);
     const int D = H * HD;

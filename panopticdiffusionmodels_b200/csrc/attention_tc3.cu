@@ -197,8 +197,8 @@ __device__ __forceinline__ void exp2_poly2(float a0, float a1, float& p0, float&
 // wait_prev: the previous P.V of this tile slot (which read P_t and wrote O_t) must have completed (o_full parity).
 template <int NCH, bool MASK>
 __device__ __forceinline__ void softmax_tile(uint32_t s_addr, uint32_t p_addr, uint32_t o_addr, int nvalid, bool first,
-                                             bool wait_prev, float& m_ref, float& l, uint64_t* s_free_bar,
-                                             uint64_t* o_full_bar, uint32_t o_full_parity, int lane) {
+                                             bool wait_prev, float& m_ref, float& l, uint32_t s_free_bar,
+                                             uint32_t o_full_bar, uint32_t o_full_parity, int lane) {
     const float cs = 0.125f * 1.4426950408889634f;  // softmax scale * log2(e)
     uint32_t s[NCH][32];
 #pragma unroll
@@ -222,7 +222,9 @@ __device__ __forceinline__ void softmax_tile(uint32_t s_addr, uint32_t p_addr, u
         }
     const float mx = fmaxf(mxa, mxb);
     if (wait_prev) {
-        ptx::mbar_wait(o_full_bar, o_full_parity);  // completed long ago, normally
+        // the previous P.V of this slot read P_t and wrote O_t: it must be complete before either is touched.  (Waiting
+        // later, just before the first P store, measured 6 % slower: the wait splits the exp2 schedule.)
+        ptx::mbar_wait(o_full_bar, o_full_parity);
         ptx::tc_fence_after();
     }
     if (first) {
@@ -466,6 +468,9 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict
         const uint32_t o_addr = tmem_base + lane_base + O_COL + t * 64;
         const int nch_last = (sh.last_n16 + 31) >> 5;  // 32-key chunks of the ragged last key tile that P.V reads
         uint32_t steps = 0;    // tile-steps of slot t completed so far (phase counter of s_full / o_full)
+        const uint32_t b_s_full = ptx::smem_u32(&s_full[t]), b_s_free = ptx::smem_u32(&s_free[t]);
+        const uint32_t b_p_full = ptx::smem_u32(&p_full[t]), b_o_full = ptx::smem_u32(&o_full[t]);
+        const uint32_t b_o_empty = ptx::smem_u32(&o_empty[t]);
 
         // The O epilogue of an item is DEFERRED until this warpgroup has pushed the first key tile of its next item
         // through the softmax: the O -> global stores then sit under the MMAs / exp2 of the neighbouring work instead
@@ -477,7 +482,7 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict
             bf16* dst = nullptr;
         } pend;
         auto flush_epilogue = [&]() {  // O / l -> bf16 rows of the pending item
-            ptx::mbar_wait(&o_full[t], pend.parity);  // the item's last P.V has landed
+            ptx::mbar_wait(b_o_full, pend.parity);  // the item's last P.V has landed
             ptx::tc_fence_after();
             TRACE(4, 0);
             if (pend.live) {
@@ -487,7 +492,7 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict
                 ptx::tmem_ld_wait();
                 ptx::tc_fence_before();
                 __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(&o_empty[t]);  // O_t may be overwritten by the next item
+                if (lane == 0) ptx::mbar_arrive(b_o_empty);  // O_t may be overwritten by the next item
                 if (pend.row_ok) {
                     const float inv = pend.inv_l;
 #pragma unroll
@@ -505,7 +510,7 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict
             } else {
                 ptx::tc_fence_before();
                 __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(&o_empty[t]);
+                if (lane == 0) ptx::mbar_arrive(b_o_empty);
             }
             pend.any = false;
             TRACE(5, 0);
@@ -524,35 +529,34 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict
                 float m_ref = 0.f, l = 0.f;
                 for (int j = 0; j < nkv; ++j) {
                     TRACE(0, steps);
-                    ptx::mbar_wait(&s_full[t], steps & 1);
+                    ptx::mbar_wait(b_s_full, steps & 1);
                     ptx::tc_fence_after();
                     TRACE(1, steps);
                     // before P_t is rewritten / O_t rescaled, the previous P.V of this slot must be complete: the previous
                     // key tile's (j > 0) or the previous item's last one (same phase the deferred epilogue waits for)
                     const bool wait_prev = j > 0 || pend.any;
-                    uint64_t* of = &o_full[t];
                     const uint32_t ofp = (steps - 1) & 1;
                     if (live) {
                         if (j < nkv - 1) {
-                            softmax_tile<4, false>(s_addr, p_addr, o_addr, KT, j == 0, wait_prev, m_ref, l, &s_free[t], of, ofp, lane);
+                            softmax_tile<4, false>(s_addr, p_addr, o_addr, KT, j == 0, wait_prev, m_ref, l, b_s_free, b_o_full, ofp, lane);
                         } else {
                             const int nv = sh.last_valid;
                             switch (nch_last) {
-                                case 1: softmax_tile<1, true>(s_addr, p_addr, o_addr, nv, j == 0, wait_prev, m_ref, l, &s_free[t], of, ofp, lane); break;
-                                case 2: softmax_tile<2, true>(s_addr, p_addr, o_addr, nv, j == 0, wait_prev, m_ref, l, &s_free[t], of, ofp, lane); break;
-                                case 3: softmax_tile<3, true>(s_addr, p_addr, o_addr, nv, j == 0, wait_prev, m_ref, l, &s_free[t], of, ofp, lane); break;
-                                default: softmax_tile<4, true>(s_addr, p_addr, o_addr, nv, j == 0, wait_prev, m_ref, l, &s_free[t], of, ofp, lane); break;
+                                case 1: softmax_tile<1, true>(s_addr, p_addr, o_addr, nv, j == 0, wait_prev, m_ref, l, b_s_free, b_o_full, ofp, lane); break;
+                                case 2: softmax_tile<2, true>(s_addr, p_addr, o_addr, nv, j == 0, wait_prev, m_ref, l, b_s_free, b_o_full, ofp, lane); break;
+                                case 3: softmax_tile<3, true>(s_addr, p_addr, o_addr, nv, j == 0, wait_prev, m_ref, l, b_s_free, b_o_full, ofp, lane); break;
+                                default: softmax_tile<4, true>(s_addr, p_addr, o_addr, nv, j == 0, wait_prev, m_ref, l, b_s_free, b_o_full, ofp, lane); break;
                             }
                         }
                         TRACE(2, steps);
                         ptx::tmem_st_wait();
                     } else {
-                        if (lane == 0) ptx::mbar_arrive(&s_free[t]);
-                        if (wait_prev) ptx::mbar_wait(of, ofp);  // keep in step with o_full
+                        if (lane == 0) ptx::mbar_arrive(b_s_free);
+                        if (wait_prev) ptx::mbar_wait(b_o_full, ofp);  // keep in step with o_full
                     }
                     ptx::tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive(&p_full[t]);
+                    if (lane == 0) ptx::mbar_arrive(b_p_full);
                     TRACE(3, steps);
                     ++steps;
                     // the previous item's epilogue, now that this item's first P is on its way (P.V of j = 0 waits for
