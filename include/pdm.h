@@ -160,6 +160,17 @@ int pdm_debug_attention(const float* qkv, float* out, int32_t nb, int32_t L, int
 int pdm_debug_layernorm(const float* x, const float* w, const float* b, float* out, int64_t rows, int32_t D,
                         int32_t precision, int32_t iters, float* ms, void* stream);
 
+/* Deferred-LayerNorm chain exactly as the bf16 engine runs a block:
+ *   x[M,D]   = resid + A[M,K1] . W1[D,K1]^T + b1      (A == NULL: x = resid; the row sums then come from the
+ *                                                      rowstats pass instead of the producing GEMM's epilogue)
+ *   out[M,N] = [gelu]( LayerNorm(x; gamma, beta, eps 1e-5) . W2[N,D]^T + b2 )     (b2 may be NULL)
+ * with the LayerNorm folded into W2 and applied per row in the consuming GEMM's epilogue.  All float32 device
+ * tensors; x_out (nullable) receives the fp32 x.  Replaces nn.LayerNorm + nn.Linear of libs/uvit_t2i.py:189-190,
+ * 209-210 (norm1 -> attn.qkv, norm2 -> mlp.fc1).  Timing of the consuming GEMM as in pdm_debug_linear. */
+int pdm_debug_ln_chain(const float* A, const float* W1, const float* b1, const float* resid, const float* gamma,
+                       const float* beta, const float* W2, const float* b2, float* out, float* x_out, int32_t M,
+                       int32_t N, int32_t D, int32_t K1, int32_t gelu, int32_t iters, float* ms, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

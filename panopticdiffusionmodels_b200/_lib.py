@@ -46,6 +46,7 @@ SIGNATURES = {
                                       C.POINTER(C.c_float), _P]),
     "pdm_debug_layernorm": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                                       C.POINTER(C.c_float), _P]),
+    "pdm_debug_ln_chain": (C.c_int, [_P] * 10 + [C.c_int32] * 6 + [C.POINTER(C.c_float), _P]),
     "pdm_last_error": (C.c_char_p, []),
     "pdm_abi_version": (C.c_int, []),
     "pdm_launch_count": (C.c_int64, []),

@@ -72,6 +72,19 @@ struct GemmProblem {
     void* out2 = nullptr;
     int out2_bs = 0;
     bool gelu = false;
+    // ---- deferred LayerNorm (tcgen05 kernel only; see gemm_tc.cu) ----
+    // producer side (fp32-output form): a second activation-dtype copy for rows >= out2b_row0 of every batch, and the
+    // per-row partial sums (sum, sum of squares) over each 128-column slice: stats[row][ceil(N/128)][2]
+    void* out2b = nullptr;
+    int out2b_bs = 0, out2b_row0 = 0, out2b_mod = 0;  // rows with (row % out2b_mod if out2b_mod else row) >= out2b_row0
+    float* stats = nullptr;
+    int stats_bs = 0;
+    float* statsb = nullptr;  // same values, second destination (rows of the concatenated mask stream)
+    int statsb_bs = 0;
+    // consumer side (bf16-output form): A1 holds the RAW rows bf16(x); W16 holds the LN-folded weight of fold_ln_weight
+    // (gamma * W, centred along K) and `bias` holds bias + W.beta, so that out = rstd * acc + bias == LN(x).W^T + b
+    const float* ln_stats = nullptr;  // [rows][ceil(K1/128)][2] written by the producer of x
+    int ln_stats_bs = 0;
 };
 
 void gemm_simt_f32(const GemmProblem& p, cudaStream_t s);
@@ -85,6 +98,11 @@ void attention_tc_bf16(const bf16* qkv, bf16* out, int nb, int L, int H, cudaStr
 void layernorm(const float* x, const float* w, const float* b, void* out, bool out_bf16, long long rows, int D,
                cudaStream_t s);
 void convert_f32_bf16(const float* in, bf16* out, long long n, cudaStream_t s);
+// deferred LayerNorm helpers: raw bf16 copy + per-row partial sums of an fp32 stream; weight folding
+void rowstats_convert(const float* x, bf16* out, float* stats, long long rows, int D, cudaStream_t s);
+void fold_ln_weight(const float* W, const float* bias, const float* gamma, const float* beta, bf16* Wf, float* d, int N,
+                    int K, cudaStream_t s);
+constexpr int LN_PART = 128;  // columns per partial-sum slice (= accumulator columns per GEMM epilogue warp)
 void copy_rows(void* dst, int dst_bs, const void* src, int src_bs, int Lr, int nb, int row_bytes, cudaStream_t s);
 
 struct EmbedArgs {

@@ -116,6 +116,92 @@ void convert_f32_bf16(const float* in, bf16* out, long long n, cudaStream_t s) {
     check_launch("convert");
 }
 
+// ----------------------------------------------------------------------------------------------
+// Deferred LayerNorm support (bf16 mode).  LN(x).W^T + b == rstd * (bf16(x).Wf^T) + (b + W.beta), Wf = centred gamma*W:
+// the GEMM that consumes LN(x) reads the RAW bf16 rows and applies mean / rstd per row in its epilogue, so the
+// LayerNorm kernel (read 4 B + write 2 B per element, 2 per block) disappears; the row sums come from the epilogue of
+// the GEMM that produced x.  rowstats_convert is the entry point of that chain (the embed output): one warp per row,
+// float4 round i of a warp covers exactly the 128-column slice i.
+// ----------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(256) rowstats_convert_kernel(const float* __restrict__ x, bf16* __restrict__ out,
+                                                               float* __restrict__ stats, long long rows, int D) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const float4* xr = reinterpret_cast<const float4*>(x + row * D);
+    const int npart = (D + LN_PART - 1) / LN_PART;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = lane + 32 * i;
+        if (i * LN_PART >= D) break;
+        float s1 = 0.f, s2 = 0.f;
+        if (c * 4 < D) {
+            const float4 v = __ldg(xr + c);
+            s1 = (v.x + v.y) + (v.z + v.w);
+            s2 = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, v.w * v.w)));
+            __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+            uint2 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&lo);
+            pk.y = *reinterpret_cast<uint32_t*>(&hi);
+            reinterpret_cast<uint2*>(out + row * D)[c] = pk;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        }
+        if (lane == 0) reinterpret_cast<float2*>(stats)[row * npart + i] = make_float2(s1, s2);
+    }
+}
+void rowstats_convert(const float* x, bf16* out, float* stats, long long rows, int D, cudaStream_t s) {
+    PDM_REQUIRE(D % 4 == 0 && D <= 2048, "rowstats_convert: D must be a multiple of 4 and <= 2048");
+    const int wpb = 8;
+    const unsigned grid = (unsigned)ceil_div_ll(rows, wpb);
+    const int nv = ceil_div(D, 128);
+    if (nv <= 4) rowstats_convert_kernel<4><<<grid, wpb * 32, 0, s>>>(x, out, stats, rows, D);
+    else if (nv <= 8) rowstats_convert_kernel<8><<<grid, wpb * 32, 0, s>>>(x, out, stats, rows, D);
+    else rowstats_convert_kernel<16><<<grid, wpb * 32, 0, s>>>(x, out, stats, rows, D);
+    check_launch("rowstats_convert");
+}
+
+// Wf[n, k] = bf16(gamma[k] * W[n, k] - m[n]),  m[n] = mean_k(gamma[k] * W[n, k]);   d[n] = bias[n] + sum_k beta[k] * W[n, k]
+// Centring along K costs nothing mathematically (sum_k (x_k - mean) * const = 0) and makes the GEMM itself subtract the row
+// mean: sum_k x_k Wf[n, k] = sum_k (x_k - mean) gamma_k W[n, k], so the consuming epilogue is a single FMA, rstd * acc + d.
+// (bf16 rounding leaves sum_k Wf[n, k] = eps_n ~ 2^-9 |w| sqrt(K/3) instead of 0: an error of (mean/std) * 1e-3 relative to
+// the output, below the bf16 rounding of the stored activation for any row whose mean is not many times its spread.)
+__global__ void __launch_bounds__(128) fold_ln_kernel(const float* __restrict__ W, const float* __restrict__ bias,
+                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                      bf16* __restrict__ Wf, float* __restrict__ d, int K) {
+    const int n = blockIdx.x;
+    float sm = 0.f, sd = 0.f;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        const float w = W[(size_t)n * K + k];
+        sm = fmaf(gamma[k], w, sm);
+        sd = fmaf(beta[k], w, sd);
+    }
+    __shared__ float red[2][4];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sm += __shfl_xor_sync(0xffffffffu, sm, o);
+        sd += __shfl_xor_sync(0xffffffffu, sd, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        red[0][threadIdx.x >> 5] = sm;
+        red[1][threadIdx.x >> 5] = sd;
+    }
+    __syncthreads();
+    const float m = ((red[0][0] + red[0][1]) + (red[0][2] + red[0][3])) / (float)K;
+    for (int k = threadIdx.x; k < K; k += blockDim.x)
+        Wf[(size_t)n * K + k] = __float2bfloat16_rn(gamma[k] * W[(size_t)n * K + k] - m);
+    if (threadIdx.x == 0) d[n] = (bias ? bias[n] : 0.f) + ((red[1][0] + red[1][1]) + (red[1][2] + red[1][3]));
+}
+void fold_ln_weight(const float* W, const float* bias, const float* gamma, const float* beta, bf16* Wf, float* d, int N,
+                    int K, cudaStream_t s) {
+    fold_ln_kernel<<<N, 128, 0, s>>>(W, bias, gamma, beta, Wf, d, K);
+    check_launch("fold_ln_weight");
+}
+
 // copy [nb, Lr, row_bytes] between buffers with different batch strides (two-stream concat)
 __global__ void copy_rows_kernel(uint4* __restrict__ dst, long long dst_bs16, const uint4* __restrict__ src,
                                  long long src_bs16, long long per_batch16, int nb) {

@@ -1,6 +1,7 @@
 // Engine: owns parameters + workspace, orchestrates the U-ViT forward (libs/uvit_t2i.py:378-525) and the
 // device-resident DPM-Solver++ loop (dpm_solver_pp.py:1018-1044 driven by train_t2i_discrete.py:387-439),
 // and exports the C ABI declared in include/pdm.h.
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -34,9 +35,16 @@ struct LinearW {
     int N = 0, K = 0;
 };
 
+// LayerNorm folded into the weight of the Linear that consumes it (bf16 mode, see elementwise.cu: fold_ln_weight)
+struct FoldW {
+    bf16* w = nullptr;   // bf16(gamma * W - mean_k(gamma * W))   [N, K]
+    float* d = nullptr;  // bias + W.beta                         [N]
+};
+
 struct BlockW {
     const float *n1w = nullptr, *n1b = nullptr, *n2w = nullptr, *n2b = nullptr;
     LinearW qkv, proj, fc1, fc2, skip;
+    FoldW qkv_f, fc1_f;
     bool has_skip = false;
 };
 
@@ -65,6 +73,8 @@ struct Workspace {
     void* u = nullptr;        // MLP hidden        [R, 4D]  act
     void* xb = nullptr;       // act copy of x     [R1, D]
     void* mxb = nullptr;      // act copy of mx    [R2, D]
+    float* stats_x = nullptr;   // [R1, ceil(D/128), 2] per-row partial (sum, sum sq) of x  (deferred LayerNorm, bf16 mode)
+    float* stats_mx = nullptr;  // [R2, ceil(D/128), 2] same for mx
     std::vector<void*> skipx; // [depth/2] [R1, D] act
     std::vector<void*> skipm; // [depth/2] [R2, D] act
     float* ctx_all = nullptr; // [nb, T, clip] fp32
@@ -108,6 +118,7 @@ struct pdm_engine {
     std::vector<BlockW> in_b, out_b, in_bm, out_bm;
     BlockW mid_b, mid_bm;
     std::vector<LinearW> zc;  // zc[li] = zero_convs[2*li+1]
+    std::map<std::string, FoldW> folds;  // keyed by "<block prefix>qkv" / "<block prefix>fc1"; allocated once (graphs bake pointers)
     LinearW ctx_lin;
     float* freqs = nullptr;
     std::vector<std::unique_ptr<Workspace>> spaces;
@@ -124,6 +135,10 @@ struct pdm_engine {
             if (kv.second.d16) cudaFree(kv.second.d16);
         }
         if (freqs) cudaFree(freqs);
+        for (auto& kv : folds) {
+            if (kv.second.w) cudaFree(kv.second.w);
+            if (kv.second.d) cudaFree(kv.second.d);
+        }
         for (auto& g : graphs)
             if (g.exec) cudaGraphExecDestroy(g.exec);
         for (auto& w : spaces)
@@ -259,6 +274,19 @@ struct pdm_engine {
         if (skip) b.skip = lin(pre + "skip_linear.weight", pre + "skip_linear.bias", D, 2 * D);
         return b;
     }
+    FoldW fold(const std::string& key, const LinearW& l, const float* gamma, const float* beta, cudaStream_t s) {
+        FoldW& f = folds[key];
+        if (!f.w) {
+            PDM_CHECK_CUDA(cudaMalloc(&f.w, (size_t)l.N * l.K * sizeof(bf16)));
+            PDM_CHECK_CUDA(cudaMalloc(&f.d, (size_t)l.N * sizeof(float)));
+        }
+        fold_ln_weight(l.w32, l.b, gamma, beta, f.w, f.d, l.N, l.K, s);
+        return f;
+    }
+    void fold_block(const std::string& pre, BlockW& b, cudaStream_t s) {
+        b.qkv_f = fold(pre + "qkv", b.qkv, b.n1w, b.n1b, s);
+        b.fc1_f = fold(pre + "fc1", b.fc1, b.n2w, b.n2b, s);
+    }
     void finalize(cudaStream_t s) {
         std::string missing;
         int nmiss = 0;
@@ -284,6 +312,16 @@ struct pdm_engine {
             }
         }
         ctx_lin = lin("context_embed.weight", "context_embed.bias", D, cfg.clip_dim);
+        for (int i = 0; i < depth / 2; ++i) {
+            fold_block("in_blocks." + std::to_string(i) + ".", in_b[i], s);
+            fold_block("out_blocks." + std::to_string(i) + ".", out_b[i], s);
+            if (two) {
+                fold_block("in_blocks_mask." + std::to_string(i) + ".", in_bm[i], s);
+                fold_block("out_blocks_mask." + std::to_string(i) + ".", out_bm[i], s);
+            }
+        }
+        fold_block("mid_block.", mid_b, s);
+        if (two) fold_block("mid_block_mask.", mid_bm, s);
         PDM_CHECK_CUDA(cudaStreamSynchronize(s));
         finalized = true;
     }
@@ -305,6 +343,9 @@ struct pdm_engine {
         w.u = a.take(R * cfg.mlp_ratio * d * act);
         w.xb = a.take(R1 * d * act);
         w.mxb = two_m ? a.take(R2 * d * act) : nullptr;
+        const size_t npart = (d + LN_PART - 1) / LN_PART;
+        w.stats_x = (float*)a.take(R1 * npart * 2 * 4);
+        w.stats_mx = two_m ? (float*)a.take(R2 * npart * 2 * 4) : nullptr;
         w.skipx.resize(depth / 2);
         w.skipm.resize(two_m ? depth / 2 : 0);
         for (auto& sp : w.skipx) sp = a.take(R1 * d * act);
@@ -453,6 +494,140 @@ struct pdm_engine {
         }
     }
 
+    // ---- bf16 mode with deferred LayerNorm ------------------------------------------------------------------
+    // No LayerNorm kernel: the qkv / fc1 GEMMs read the RAW bf16 copy of the residual stream (`cur`, or ws.h after the
+    // skip GEMM / proj) with LN folded into their weights and apply mean / rstd per row in the epilogue; the row sums
+    // (`stats`) are produced by the epilogue of whichever GEMM wrote the fp32 stream last.
+    //   cur      bf16 copy of x on entry (ignored by blocks with a long skip: their skip GEMM emits it into ws.h)
+    //   out2     where fc2 leaves the bf16 copy of the block output (nullptr: nobody reads it)
+    //   out2b    optional second copy for rows >= out2b_row0 (tail of the concatenated mask stream)
+    //   out_stats  fc2 also refreshes `stats` (the next consumer is an LN-folded GEMM, not a skip GEMM)
+    void run_block_dln(const BlockW& w, Workspace& ws, float* x, float* stats, const void* cur, int nb, int Lx,
+                       const void* skipA1, const void* skipA2, void* out2, void* out2b, int out2b_row0, bool out_stats,
+                       cudaStream_t s) {
+        const int R = nb * Lx;
+        if (w.has_skip) {
+            Scope sc(this, "gemm_skip", s);
+            GemmProblem g;
+            g.A1 = skipA1; g.K1 = D; g.A2 = skipA2; g.K2 = D;
+            g.W16 = w.skip.w16; g.bias = w.skip.b; g.N = D;
+            g.nb = 1; g.Lr = R; g.out32 = x; g.out2 = ws.h; g.stats = stats;
+            gemm_tc_bf16(g, s);
+            cur = ws.h;
+        }
+        {
+            Scope sc(this, "gemm_qkv", s);
+            GemmProblem g;
+            g.A1 = cur; g.K1 = D; g.W16 = w.qkv_f.w; g.bias = w.qkv_f.d; g.ln_stats = stats;
+            g.N = 3 * D; g.nb = 1; g.Lr = R; g.out2 = ws.qkv;
+            gemm_tc_bf16(g, s);
+        }
+        {
+            Scope sc(this, "attention", s);
+            attention_tc_bf16((const bf16*)ws.qkv, (bf16*)ws.ao, nb, Lx, H, s);
+        }
+        {
+            Scope sc(this, "gemm_proj", s);
+            GemmProblem g;
+            g.A1 = ws.ao; g.K1 = D; g.W16 = w.proj.w16; g.bias = w.proj.b; g.N = D;
+            g.nb = 1; g.Lr = R; g.resid = x; g.out32 = x; g.out2 = ws.h; g.stats = stats;
+            gemm_tc_bf16(g, s);
+        }
+        {
+            Scope sc(this, "gemm_fc1", s);
+            GemmProblem g;
+            g.A1 = ws.h; g.K1 = D; g.W16 = w.fc1_f.w; g.bias = w.fc1_f.d; g.ln_stats = stats;
+            g.N = w.fc1.N; g.nb = 1; g.Lr = R; g.out2 = ws.u; g.gelu = true;
+            gemm_tc_bf16(g, s);
+        }
+        {
+            Scope sc(this, "gemm_fc2", s);
+            GemmProblem g;
+            g.A1 = ws.u; g.K1 = w.fc2.K; g.W16 = w.fc2.w16; g.bias = w.fc2.b; g.N = D;
+            g.nb = 1; g.Lr = R; g.resid = x; g.out32 = x; g.out2 = out2;
+            g.out2b = out2b; g.out2b_row0 = out2b_row0; g.out2b_mod = Lx;  // flat rows: the filter is per sample
+            g.stats = out_stats ? stats : nullptr;
+            gemm_tc_bf16(g, s);
+        }
+    }
+
+    // x += zero_conv(A[:, :L1]) with A = bf16 copy of the mask-block output [nb, L2, D]  (libs/uvit_t2i.py:432-436).
+    //   out2       bf16 copy of the new x (long-skip operand / A of the next image block), may be null
+    //   to_mask    the NEXT layer's mask block starts from cat(x, m): also store the new x rows into mx[:, :L1] (fp32,
+    //              only if fp32_concat: the next mask block updates mx in place), into ws.mxb[:, :L1] (bf16) and their
+    //              row sums into stats_mx -- the concat of libs/uvit_t2i.py:427 never runs as a kernel
+    void run_zero_conv_dln(const LinearW& z, Workspace& ws, const void* A, void* out2, int nb, bool to_mask,
+                           bool fp32_concat, bool out_stats, cudaStream_t s) {
+        Scope sc(this, "gemm_zeroconv", s);
+        GemmProblem g;
+        g.A1 = A; g.K1 = D; g.a1_bs = L2;
+        g.W16 = z.w16; g.bias = z.b; g.N = D;
+        g.nb = nb; g.Lr = L1;
+        g.resid = ws.x; g.resid_bs = L1; g.out32 = ws.x; g.out32_bs = L1; g.out2 = out2; g.out2_bs = L1;
+        if (out_stats) {
+            g.stats = ws.stats_x; g.stats_bs = L1;
+        }
+        if (to_mask) {
+            g.out2b = ws.mxb; g.out2b_bs = L2; g.out2b_row0 = 0;
+            if (fp32_concat) {
+                g.out32b = ws.mx; g.out32b_bs = L2;
+            }
+            if (out_stats) {
+                g.statsb = ws.stats_mx; g.statsb_bs = L2;
+            }
+        }
+        gemm_tc_bf16(g, s);
+    }
+
+    void blocks_dln(Workspace& ws, int nb, int Lx, bool two_m, cudaStream_t s) {
+        const int half = depth / 2;
+        {
+            Scope sc(this, "layernorm", s);  // the only remaining row-statistics pass: the embed output
+            rowstats_convert(ws.x, (bf16*)ws.xb, ws.stats_x, (long long)nb * Lx, D, s);
+        }
+        if (!two_m) {
+            const void* cur = ws.xb;
+            for (int i = 0; i < half; ++i) {
+                run_block_dln(in_b[i], ws, ws.x, ws.stats_x, cur, nb, Lx, nullptr, nullptr, ws.skipx[i], nullptr, 0, true, s);
+                cur = ws.skipx[i];
+            }
+            run_block_dln(mid_b, ws, ws.x, ws.stats_x, cur, nb, Lx, nullptr, nullptr, ws.xb, nullptr, 0, false, s);
+            for (int j = 0; j < half; ++j)
+                run_block_dln(out_b[j], ws, ws.x, ws.stats_x, nullptr, nb, Lx, ws.xb, ws.skipx[half - 1 - j],
+                              j + 1 < half ? ws.xb : nullptr, nullptr, 0, false, s);
+            return;
+        }
+        {
+            Scope sc(this, "concat", s);  // mx[:, :L1] = x: the only concat that runs as a kernel
+            copy_rows(ws.mx, L2, ws.x, L1, L1, nb, D * 4, s);
+        }
+        {
+            Scope sc(this, "layernorm", s);
+            rowstats_convert(ws.mx, (bf16*)ws.mxb, ws.stats_mx, (long long)nb * L2, D, s);
+        }
+        const void* cur_x = ws.xb;
+        int li = 0;
+        for (int i = 0; i < half; ++i, ++li) {
+            run_block_dln(in_b[i], ws, ws.x, ws.stats_x, cur_x, nb, L1, nullptr, nullptr, nullptr, nullptr, 0, false, s);
+            run_block_dln(in_bm[i], ws, ws.mx, ws.stats_mx, ws.mxb, nb, L2, nullptr, nullptr, ws.skipm[i], ws.mxb, L1, true, s);
+            run_zero_conv_dln(zc[li], ws, ws.skipm[i], ws.skipx[i], nb, true, true, true, s);
+            cur_x = ws.skipx[i];
+        }
+        // mid layer: its outputs feed skip GEMMs (no LayerNorm on them) -> bf16 copies only
+        run_block_dln(mid_b, ws, ws.x, ws.stats_x, cur_x, nb, L1, nullptr, nullptr, nullptr, nullptr, 0, false, s);
+        run_block_dln(mid_bm, ws, ws.mx, ws.stats_mx, ws.mxb, nb, L2, nullptr, nullptr, ws.h, ws.mxb, L1, false, s);
+        run_zero_conv_dln(zc[li], ws, ws.h, ws.xb, nb, true, false, false, s);
+        ++li;
+        for (int j = 0; j < half; ++j, ++li) {
+            const bool more = j + 1 < half;
+            run_block_dln(out_b[j], ws, ws.x, ws.stats_x, nullptr, nb, L1, ws.xb, ws.skipx[half - 1 - j], nullptr, nullptr, 0,
+                          false, s);
+            run_block_dln(out_bm[j], ws, ws.mx, ws.stats_mx, nullptr, nb, L2, ws.mxb, ws.skipm[half - 1 - j], ws.h,
+                          more ? ws.mxb : nullptr, L1, false, s);
+            run_zero_conv_dln(zc[li], ws, ws.h, more ? ws.xb : nullptr, nb, more, false, false, s);
+        }
+    }
+
     // x += zero_conv(mx_act[:, :L1])  (libs/uvit_t2i.py:432-436); also emits the activation copy of x
     // also_mx: additionally store the updated x rows into mx[:, :L1] -- the concat of the next layer, fused (bf16 mode)
     void run_zero_conv(const LinearW& z, Workspace& ws, const void* mx_act, void* out2, int nb, int prec,
@@ -508,7 +683,10 @@ struct pdm_engine {
         }
         const int half = depth / 2;
         const size_t actsz = b16 ? 2 : 4;
-        if (!two_m) {
+        static const bool dln = getenv("PDM_NO_DLN") == nullptr;  // A/B switch: the LayerNorm-kernel path of round 1a
+        if (b16 && dln) {
+            blocks_dln(ws, nb, Lx, two_m, s);
+        } else if (!two_m) {
             for (int i = 0; i < half; ++i) run_block(in_b[i], ws, ws.x, nb, Lx, nullptr, nullptr, ws.skipx[i], prec, s);
             run_block(mid_b, ws, ws.x, nb, Lx, nullptr, nullptr, ws.xb, prec, s);
             for (int j = 0; j < half; ++j)
@@ -853,6 +1031,12 @@ int pdm_debug_linear(const float* A, const float* A2, const float* W, const floa
         g.K1 = K; g.K2 = A2 ? K2 : 0; g.N = N; g.nb = 1; g.Lr = M; g.bias = bias; g.gelu = (gelu & 1) != 0;
         const bool out16 = (gelu & 2) != 0 && precision == PDM_PREC_BF16 && !resid;  // bf16-only output (qkv / fc1 form)
         g.out32 = out;
+        const bool emit = (gelu & 4) != 0 && precision == PDM_PREC_BF16 && !out16;  // + bf16 copy and LayerNorm row sums
+        DevBuf xb16(emit ? (size_t)M * N * 2 : 0), st(emit ? (size_t)M * ((N + LN_PART - 1) / LN_PART) * 8 : 0);
+        if (emit) {
+            g.out2 = xb16.p;
+            g.stats = (float*)st.p;
+        }
         if (resid) {  // the production kernels update the fp32 residual stream in place
             PDM_CHECK_CUDA(cudaMemcpyAsync(out, resid, (size_t)M * N * sizeof(float), cudaMemcpyDeviceToDevice, s));
             g.resid = out;
@@ -923,6 +1107,43 @@ int pdm_debug_layernorm(const float* x, const float* w, const float* b, float* o
             check_launch("bf16_to_f32");
             PDM_CHECK_CUDA(cudaStreamSynchronize(s));
         }
+    });
+}
+
+int pdm_debug_ln_chain(const float* A, const float* W1, const float* b1, const float* resid, const float* gamma,
+                       const float* beta, const float* W2, const float* b2, float* out, float* x_out, int32_t M,
+                       int32_t N, int32_t D, int32_t K1, int32_t gelu, int32_t iters, float* ms, void* stream) {
+    return guard([&] {
+        PDM_REQUIRE(resid && gamma && beta && W2 && out && M > 0 && N > 0 && D > 0, "bad argument");
+        PDM_REQUIRE(!A || (W1 && K1 > 0), "A needs W1 / K1");
+        cudaStream_t s = (cudaStream_t)stream;
+        const int npart = (D + LN_PART - 1) / LN_PART;
+        DevBuf x((size_t)M * D * 4), xb((size_t)M * D * 2), stats((size_t)M * npart * 8);
+        DevBuf wf((size_t)N * D * 2), d((size_t)N * 4), o16((size_t)M * N * 2);
+        PDM_CHECK_CUDA(cudaMemcpyAsync(x.p, resid, (size_t)M * D * 4, cudaMemcpyDeviceToDevice, s));
+        if (A) {
+            DevBuf a16((size_t)M * K1 * 2), w16((size_t)D * K1 * 2);
+            convert_f32_bf16(A, (bf16*)a16.p, (long long)M * K1, s);
+            convert_f32_bf16(W1, (bf16*)w16.p, (long long)D * K1, s);
+            GemmProblem g;
+            g.A1 = a16.p; g.K1 = K1; g.W16 = (const bf16*)w16.p; g.bias = b1; g.N = D; g.nb = 1; g.Lr = M;
+            g.resid = (float*)x.p; g.out32 = (float*)x.p; g.out2 = xb.p; g.stats = (float*)stats.p;
+            gemm_tc_bf16(g, s);
+            PDM_CHECK_CUDA(cudaStreamSynchronize(s));  // a16 / w16 go out of scope
+        } else {
+            rowstats_convert((const float*)x.p, (bf16*)xb.p, (float*)stats.p, M, D, s);
+        }
+        fold_ln_weight(W2, b2, gamma, beta, (bf16*)wf.p, (float*)d.p, N, D, s);
+        GemmProblem g;
+        g.A1 = xb.p; g.K1 = D; g.W16 = (const bf16*)wf.p; g.bias = (const float*)d.p;
+        g.ln_stats = (const float*)stats.p; g.N = N; g.nb = 1; g.Lr = M; g.out2 = o16.p; g.gelu = gelu != 0;
+        gemm_tc_bf16(g, s);
+        time_kernel([&] { gemm_tc_bf16(g, s); }, iters, ms, s);
+        bf16_to_f32_kernel<<<(unsigned)ceil_div_ll((long long)M * N, 256), 256, 0, s>>>((const bf16*)o16.p, out,
+                                                                                       (long long)M * N);
+        check_launch("bf16_to_f32");
+        if (x_out) PDM_CHECK_CUDA(cudaMemcpyAsync(x_out, x.p, (size_t)M * D * 4, cudaMemcpyDeviceToDevice, s));
+        PDM_CHECK_CUDA(cudaStreamSynchronize(s));
     });
 }
 

@@ -41,7 +41,11 @@ constexpr int NBLK = WCOLS / 32;               // 32-column blocks per epilogue 
 constexpr int THREADS = 64 + EPI_WARPS * 32;
 constexpr int A_BYTES = BM * BK * 2;
 constexpr int SCR_STRIDE = 36;  // 32-bit words per scratch row: 128 B payload + 16 B pad (16 B aligned, conflict-free)
-constexpr int SCR_WORDS = 32 * SCR_STRIDE + WCOLS;  // + this warp's slice of the bias vector
+constexpr int LN_MAXPART = 8;   // LayerNorm-consuming form: K <= 8 * 128
+// + this warp's slice of the bias and LN column-sum vectors + a [32 lanes][LN_MAXPART] float2 landing zone for the
+// row sums of the NEXT tile (cp.async)
+constexpr int SCR_WORDS = 32 * SCR_STRIDE + 2 * WCOLS + 32 * LN_MAXPART * 2;
+static_assert(WCOLS == LN_PART, "the LayerNorm partial sums are per epilogue-warp column slice");
 constexpr int SCR_BYTES = SCR_WORDS * 4;
 constexpr uint32_t TMEM_COLS = 512;
 
@@ -67,6 +71,20 @@ struct TcParams {
     bf16* out2;       // bf16 output (nullptr: none)
     long long out2_bs;
     int gelu;
+    // deferred LayerNorm, producer side (fp32 form)
+    bf16* out2b;      // second bf16 copy, rows >= out2b_row0 of each batch only
+    long long out2b_bs;
+    int out2b_row0, out2b_mod;  // row filter: (row % out2b_mod if out2b_mod else row) >= out2b_row0
+    float* stats;     // [rows][npart][2] partial (sum, sum of squares) per WCOLS-column slice
+    long long stats_bs;
+    float* statsb;
+    long long statsb_bs;
+    int npart;        // ceil(N / WCOLS)
+    // deferred LayerNorm, consumer side (bf16 form): out = rstd * (acc - mean * ln_c[n]) + bias[n]
+    const float* ln_stats;
+    long long ln_bs;
+    int ln_npart;     // ceil(K / WCOLS)
+    float ln_invK;
 };
 
 // GELU(erf) for the bf16 path (libs/timm.py:101 -> nn.GELU()).  x.Phi(x) = 0.5 x (1 + tanh(x (a + b x^2 + c x^4)))
@@ -109,6 +127,22 @@ __device__ __forceinline__ void gelu_fast2(float& x0, float& x1) {
     asm("fma.rn.f32x2 %0, %1, %2, %1;" : "=l"(r) : "l"(hx), "l"(t));
     asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(r));
 }
+// deferred LayerNorm on a column pair: x = rstd * x + d   (one packed fp32x2 FMA; the mean term is gone because the
+// folded weight is centred along K, see fold_ln_weight)
+__device__ __forceinline__ void scale_add2(float& x0, float& x1, uint64_t s2, float d0, float d1) {
+    uint64_t x, d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(x0), "f"(x1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(d0), "f"(d1));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(x) : "l"(s2), "l"(x), "l"(d));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(x));
+}
+__device__ __forceinline__ void add2(float& x0, float& x1, float d0, float d1) {
+    uint64_t x, d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(x0), "f"(x1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(d0), "f"(d1));
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(x) : "l"(x), "l"(d));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(x));
+}
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&v);
@@ -124,7 +158,11 @@ __device__ __forceinline__ void release_accumulator(uint64_t* tempty_bar, uint32
     }
 }
 
-template <int NCTA>
+// EPI selects the epilogue at compile time (straight-line code per form: the epilogue is latency-bound with two warps per
+// scheduler, and runtime flags put a branch around every 8-column group, which kept the compiler from overlapping them)
+enum { EPI_F32 = 0, EPI_PACK = 1, EPI_LN = 2, EPI_LN_GELU = 3, EPI_F32_EMIT = 4 };  // _EMIT: + row sums / out2b (deferred LayerNorm producer)
+
+template <int NCTA, int EPI>
 __global__ void __cluster_dims__(NCTA, 1, 1) __launch_bounds__(THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmB, const TcParams p) {
@@ -270,8 +308,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         const int q = warp & 3;    // TMEM lane quarter this warp may access
         const int half = ew >> 2;  // which WCOLS-column slice of the tile
         uint32_t* scr = reinterpret_cast<uint32_t*>(scr_base + ew * SCR_BYTES);
-        float* sbias = reinterpret_cast<float*>(scr + 32 * SCR_STRIDE);  // [128]
-        const bool packed = (p.out32 == nullptr) && ((p.N & 7) == 0);
+        float* sbias = reinterpret_cast<float*>(scr + 32 * SCR_STRIDE);  // [WCOLS]
+        float2* sstat = reinterpret_cast<float2*>(sbias + WCOLS) + lane * LN_MAXPART;  // this lane's row sums (cp.async)
+        constexpr bool packed = EPI != EPI_F32 && EPI != EPI_F32_EMIT;
+        constexpr bool EMIT = EPI == EPI_F32_EMIT;
+        constexpr bool LN = EPI == EPI_LN || EPI == EPI_LN_GELU;
+        // the partial row sums of a tile are fetched one tile ahead: read at the top of a tile they cost a full L2 / HBM
+        // round trip during which the finished accumulator sat unread (measured: qkv / fc1 27-30 % slower)
+        auto prefetch_stats = [&](int tile) {
+            if (tile < p.total_tiles) {
+                const int mp = tile / p.ntn;
+                const int mt = NCTA * mp + (int)rank;
+                if (mt < p.n_mtiles) {
+                    const int b = mt / p.tpb;
+                    const int t = (mt - b * p.tpb) * BM + q * 32 + lane;
+                    if (t < p.Lr) {
+                        const float2* sp = reinterpret_cast<const float2*>(p.ln_stats) + ((long long)b * p.ln_bs + t) * p.ln_npart;
+                        const uint32_t dst = ptx::smem_u32(sstat);
+                        for (int i = 0; i < p.ln_npart; ++i)
+                            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 8 * i), "l"(sp + i) : "memory");
+                    }
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        if (LN) prefetch_stats(unit_id);
         const int rsub = lane >> 3, c8 = lane & 7;
         int it = 0;
         for (int tile = unit_id; tile < p.total_tiles; tile += n_units, ++it) {
@@ -286,14 +347,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
             const int trow0 = t0 + q * 32;
             const int ncol0 = nt * BN + half * WCOLS;  // first column of this warp's slice
             const uint32_t tbase = tmem_base + (uint32_t(q * 32) << 16) + as * BN + half * WCOLS;
-            if (packed) {
+            if constexpr (packed) {
                 // ---- bf16-only output: 2 chunks of 64 columns; bias/GELU in the row domain, pack, transpose ----
-                if (p.bias) {
+                const bool has_bias = LN || p.bias != nullptr;
+                const bool gelu = LN ? (EPI == EPI_LN_GELU) : (p.gelu != 0);
+                if (has_bias) {
 #pragma unroll
                     for (int i = 0; i < NBLK; ++i) {
                         const int c = ncol0 + lane + 32 * i;
                         sbias[lane + 32 * i] = c < p.N ? __ldg(p.bias + c) : 0.f;
                     }
+                }
+                // deferred LayerNorm: this thread owns accumulator row trow0 + lane -> its mean / rstd from the partial
+                // sums the producer of x left behind (read before the accumulator is waited for)
+                uint64_t rstd2 = 0;
+                if constexpr (LN) {
+                    float rstd = 0.f;
+                    asm volatile("cp.async.wait_group 0;" ::: "memory");
+                    if (trow0 + lane < lr_eff) {
+                        float a1 = 0.f, a2 = 0.f;
+                        for (int i = 0; i < p.ln_npart; ++i) {
+                            const float2 t = sstat[i];
+                            a1 += t.x;
+                            a2 += t.y;
+                        }
+                        const float mean = a1 * p.ln_invK;
+                        const float var = fmaxf(fmaf(-mean, mean, a2 * p.ln_invK), 0.f);
+                        rstd = rsqrtf(var + 1e-5f);
+                    }
+                    asm("mov.b64 %0, {%1, %1};" : "=l"(rstd2) : "f"(rstd));
+                    prefetch_stats(tile + n_units);
                 }
                 __syncwarp();
                 ptx::mbar_wait(&tfull[as], aphase);
@@ -308,9 +391,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
                 for (int blk = 0; blk < NBLK; ++blk) {
                     const int chunk = blk >> 1, hh = blk & 1;
                     float4 bv[8];
-                    if (p.bias) {
+                    if (has_bias) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) bv[i] = *reinterpret_cast<const float4*>(sbias + blk * 32 + 4 * i);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) bv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                     }
                     ptx::tmem_ld_wait();
                     if (blk < NBLK - 1) ptx::tmem_ld_32x32(tbase + (blk + 1) * 32, v[(blk + 1) & 1]);
@@ -320,12 +406,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
                         float f[8];
 #pragma unroll
                         for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[blk & 1][8 * j + e]);
-                        if (p.bias) {
+                        {
                             const float4 b0 = bv[2 * j], b1 = bv[2 * j + 1];
-                            f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-                            f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+                            if constexpr (LN) {
+                                scale_add2(f[0], f[1], rstd2, b0.x, b0.y);
+                                scale_add2(f[2], f[3], rstd2, b0.z, b0.w);
+                                scale_add2(f[4], f[5], rstd2, b1.x, b1.y);
+                                scale_add2(f[6], f[7], rstd2, b1.z, b1.w);
+                            } else if (has_bias) {
+                                add2(f[0], f[1], b0.x, b0.y);
+                                add2(f[2], f[3], b0.z, b0.w);
+                                add2(f[4], f[5], b1.x, b1.y);
+                                add2(f[6], f[7], b1.z, b1.w);
+                            }
                         }
-                        if (p.gelu) {
+                        if (gelu) {
 #pragma unroll
                             for (int e = 0; e < 8; e += 2) gelu_fast2(f[e], f[e + 1]);
                         }
@@ -356,6 +451,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
                 float* o32 = p.out32 + ((long long)b * p.out32_bs + trow0 + rsub) * p.N + colq;
                 float* o32b = p.out32b ? p.out32b + ((long long)b * p.out32b_bs + trow0 + rsub) * p.N + colq : nullptr;
                 bf16* o16 = p.out2 ? p.out2 + ((long long)b * p.out2_bs + trow0 + rsub) * p.N + colq : nullptr;
+                bf16* o16b = p.out2b ? p.out2b + ((long long)b * p.out2b_bs + trow0 + rsub) * p.N + colq : nullptr;
+                uint32_t okb = 0;  // bit ps: row ps * 4 + rsub passes the out2b row filter
+                if (o16b) {
+#pragma unroll
+                    for (int ps = 0; ps < 8; ++ps) {
+                        int t = trow0 + ps * 4 + rsub;
+                        if (p.out2b_mod) t %= p.out2b_mod;
+                        okb |= (t >= p.out2b_row0 ? 1u : 0u) << ps;
+                    }
+                }
+                float s1[8], s2[8];  // deferred LayerNorm: this lane's share of the row sums over the warp's column slice
+#pragma unroll
+                for (int ps = 0; ps < 8; ++ps) s1[ps] = s2[ps] = 0.f;
                 float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);  // bias of the current chunk (next one is prefetched)
                 if (p.bias && colq < p.N) bb = __ldg(reinterpret_cast<const float4*>(p.bias + colq));
                 // residual rows of chunk 0, fetched before the accumulator is even ready
@@ -389,6 +497,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
                     float* po = o32 + 32 * chunk;
                     float* pob = o32b ? o32b + 32 * chunk : nullptr;
                     bf16* ph = o16 ? o16 + 32 * chunk : nullptr;
+                    bf16* phb = o16b ? o16b + 32 * chunk : nullptr;
 #pragma unroll
                     for (int ps = 0; ps < 8; ++ps) {
                         const int r = ps * 4 + rsub;
@@ -401,19 +510,53 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
                         if (p.accumulate) {
                             a.x += res[ps].x; a.y += res[ps].y; a.z += res[ps].z; a.w += res[ps].w;
                             // software pipeline: fetch the same row of the NEXT chunk into the slot just consumed
+                            // (two chunks ahead, and an L2 bulk prefetch of the next tile's slice, both measured SLOWER)
                             if (next_ok && row_ok) res[ps] = *reinterpret_cast<const float4*>(po + 32);
                         }
                         if (col_ok && row_ok) {
                             *reinterpret_cast<float4*>(po) = a;
                             if (pob) *reinterpret_cast<float4*>(pob) = a;
                             if (ph) *reinterpret_cast<uint2*>(ph) = make_uint2(pack2(a.x, a.y), pack2(a.z, a.w));
+                            if constexpr (EMIT) {
+                                if ((okb >> ps) & 1u) *reinterpret_cast<uint2*>(phb) = make_uint2(pack2(a.x, a.y), pack2(a.z, a.w));
+                                s1[ps] += (a.x + a.y) + (a.z + a.w);
+                                s2[ps] = fmaf(a.x, a.x, fmaf(a.y, a.y, fmaf(a.z, a.z, fmaf(a.w, a.w, s2[ps]))));
+                            }
                         }
                         po += rstep;
                         if (pob) pob += rstep;
                         if (ph) ph += rstep;
+                        if constexpr (EMIT) {
+                            if (phb) phb += rstep;
+                        }
                     }
                     bb = bb_next;
                     __syncwarp();
+                }
+                if constexpr (EMIT) if (p.stats) {
+                    // the 8 lanes that share a row (same rsub) combine their shares; lane (rsub, c8) then stores row 4*c8 + rsub
+                    float w1 = 0.f, w2 = 0.f;
+#pragma unroll
+                    for (int ps = 0; ps < 8; ++ps) {
+#pragma unroll
+                        for (int o = 1; o < 8; o <<= 1) {
+                            s1[ps] += __shfl_xor_sync(0xffffffffu, s1[ps], o);
+                            s2[ps] += __shfl_xor_sync(0xffffffffu, s2[ps], o);
+                        }
+                        if (c8 == ps) {
+                            w1 = s1[ps];
+                            w2 = s2[ps];
+                        }
+                    }
+                    const int r = c8 * 4 + rsub;
+                    if (ncol0 < p.N && trow0 + r < lr_eff) {
+                        const int part = ncol0 / WCOLS;
+                        reinterpret_cast<float2*>(p.stats)[((long long)b * p.stats_bs + trow0 + r) * p.npart + part] =
+                            make_float2(w1, w2);
+                        if (p.statsb)
+                            reinterpret_cast<float2*>(p.statsb)[((long long)b * p.statsb_bs + trow0 + r) * p.npart + part] =
+                                make_float2(w1, w2);
+                    }
                 }
             }
         }
@@ -461,7 +604,7 @@ int num_sms() {
     return n;
 }
 
-template <int NCTA>
+template <int NCTA, int EPI>
 void launch(const GemmProblem& g, cudaStream_t s) {
     const int K2 = g.A2 ? g.K2 : 0;
     const int K = g.K1 + K2;
@@ -483,18 +626,31 @@ void launch(const GemmProblem& g, cudaStream_t s) {
     p.out2 = (bf16*)g.out2;
     p.out2_bs = g.out2_bs ? g.out2_bs : g.Lr;
     p.gelu = g.gelu ? 1 : 0;
+    p.out2b = (bf16*)g.out2b;
+    p.out2b_bs = g.out2b_bs ? g.out2b_bs : g.Lr;
+    p.out2b_row0 = g.out2b_row0;
+    p.out2b_mod = g.out2b_mod;
+    p.stats = g.stats;
+    p.stats_bs = g.stats_bs ? g.stats_bs : g.Lr;
+    p.statsb = g.statsb;
+    p.statsb_bs = g.statsb_bs ? g.statsb_bs : g.Lr;
+    p.npart = ceil_div(g.N, WCOLS);
+    p.ln_stats = g.ln_stats;
+    p.ln_bs = g.ln_stats_bs ? g.ln_stats_bs : g.Lr;
+    p.ln_npart = ceil_div(g.K1, WCOLS);
+    p.ln_invK = 1.f / (float)g.K1;
     const CUtensorMap tmA1 = make_tmap_bf16_3d(g.A1, g.K1, g.Lr, g.nb, g.a1_bs ? g.a1_bs : g.Lr, BM, BK);
     const CUtensorMap tmA2 =
         g.A2 ? make_tmap_bf16_3d(g.A2, g.K2, g.Lr, g.nb, g.a2_bs ? g.a2_bs : g.Lr, BM, BK) : tmA1;
     const CUtensorMap tmB = make_tmap_bf16_3d(g.W16, K, g.N, 1, g.N, BN / NCTA, BK);
     static bool attr_set = false;
     if (!attr_set) {
-        PDM_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<NCTA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        PDM_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<NCTA, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             Cfg<NCTA>::SMEM_BYTES));
         attr_set = true;
     }
     const int units = std::max(1, std::min(p.total_tiles, num_sms() / NCTA));
-    gemm_tc_kernel<NCTA><<<NCTA * units, THREADS, Cfg<NCTA>::SMEM_BYTES, s>>>(tmA1, tmA2, tmB, p);
+    gemm_tc_kernel<NCTA, EPI><<<NCTA * units, THREADS, Cfg<NCTA>::SMEM_BYTES, s>>>(tmA1, tmA2, tmB, p);
     check_launch("gemm_tc");
 }
 
@@ -538,8 +694,27 @@ void gemm_tc_bf16(const GemmProblem& g, cudaStream_t s) {
     PDM_REQUIRE(!g.out32b || g.out32, "gemm_tc: out32b needs out32");
     PDM_REQUIRE(!g.resid || (g.resid == g.out32 && (g.resid_bs ? g.resid_bs : g.Lr) == (g.out32_bs ? g.out32_bs : g.Lr)),
                 "gemm_tc: the residual must be the fp32 output (in-place accumulate)");
+    PDM_REQUIRE(!g.ln_stats || g.K1 <= LN_MAXPART * WCOLS, "gemm_tc: the LayerNorm-consuming form supports K <= 1024");
+    PDM_REQUIRE(!g.ln_stats || (g.bias && !g.A2 && !g.out32 && g.N % 8 == 0),
+                "gemm_tc: the LayerNorm-consuming form needs the folded bias, a single A and a bf16-only output");
+    PDM_REQUIRE(g.out32 || g.N % 8 == 0, "gemm_tc: the bf16-only output form needs N % 8 == 0");
+    PDM_REQUIRE((!g.stats && !g.statsb && !g.out2b) || g.out32, "gemm_tc: row sums / out2b belong to the fp32-output form");
+    PDM_REQUIRE(!g.statsb || g.stats, "gemm_tc: statsb needs stats");
     static const bool one_cta = getenv("PDM_GEMM_1CTA") != nullptr;
-    if (one_cta) launch<1>(g, s); else launch<2>(g, s);
+    const int epi = g.out32 ? ((g.stats || g.out2b) ? EPI_F32_EMIT : EPI_F32) : (g.ln_stats ? (g.gelu ? EPI_LN_GELU : EPI_LN) : EPI_PACK);
+    if (one_cta) {
+        if (epi == EPI_F32) launch<1, EPI_F32>(g, s);
+        else if (epi == EPI_F32_EMIT) launch<1, EPI_F32_EMIT>(g, s);
+        else if (epi == EPI_PACK) launch<1, EPI_PACK>(g, s);
+        else if (epi == EPI_LN) launch<1, EPI_LN>(g, s);
+        else launch<1, EPI_LN_GELU>(g, s);
+    } else {
+        if (epi == EPI_F32) launch<2, EPI_F32>(g, s);
+        else if (epi == EPI_F32_EMIT) launch<2, EPI_F32_EMIT>(g, s);
+        else if (epi == EPI_PACK) launch<2, EPI_PACK>(g, s);
+        else if (epi == EPI_LN) launch<2, EPI_LN>(g, s);
+        else launch<2, EPI_LN_GELU>(g, s);
+    }
 }
 
 }  // namespace pdm

@@ -60,7 +60,25 @@ def main():
         print(json.dumps(out[-1]), flush=True)
         del A, A2, W, o, r
 
+    def ln_gemm(name, N, gelu):
+        x = torch.randn(M, D, device=dev)
+        gam, bet = torch.rand(D, device=dev) + 0.5, torch.randn(D, device=dev) * 0.1
+        W = torch.randn(N, D, device=dev) * 0.02
+        b = torch.randn(N, device=dev)
+        o = torch.empty(M, N, device=dev)
+        _lib.check(lib.pdm_debug_ln_chain(None, None, None, _lib.ptr(x), _lib.ptr(gam), _lib.ptr(bet), _lib.ptr(W),
+                                          _lib.ptr(b), _lib.ptr(o), None, M, N, D, 0, gelu, a.iters, C.byref(ms), s))
+        fl = 2.0 * M * N * D
+        print(json.dumps(dict(kernel=name, M=M, N=N, K=D, ms=round(ms.value, 4), tflops=round(fl / ms.value / 1e9, 1),
+                              frac_of_bf16_peak=round(fl / ms.value / 1e9 / tf, 3), peak_src=src)), flush=True)
+
     only = set(a.only.split(",")) if a.only else {"gemm", "layernorm", "attention"}
+    if "gemm" in only:
+        ln_gemm("LN+gemm_qkv(bf16 out)", 3 * D, 0)
+        ln_gemm("LN+gemm_fc1(+gelu, bf16 out)", 4 * D, 1)
+        gemm("gemm_proj(+resid, +bf16 copy, +row sums)", D, D, gelu=4, resid=True)
+        gemm("gemm_fc2(+resid, +bf16 copy, +row sums)", D, 4 * D, gelu=4, resid=True)
+        gemm("gemm_skip(+bf16 copy, +row sums)", D, D, K2=D, gelu=4)
     if "gemm" in only:
         gemm("gemm_qkv(bf16 out)", 3 * D, D, gelu=2)
         gemm("gemm_proj(+resid)", D, D, resid=True)
