@@ -75,6 +75,7 @@ struct Workspace {
     void* mxb = nullptr;      // act copy of mx    [R2, D]
     float* stats_x = nullptr;   // [R1, ceil(D/128), 2] per-row partial (sum, sum sq) of x  (deferred LayerNorm, bf16 mode)
     float* stats_mx = nullptr;  // [R2, ceil(D/128), 2] same for mx
+    float* rstd = nullptr;      // [max(R1, R2)] 1 / std of the rows the next LN-folded GEMM consumes
     std::vector<void*> skipx; // [depth/2] [R1, D] act
     std::vector<void*> skipm; // [depth/2] [R2, D] act
     float* ctx_all = nullptr; // [nb, T, clip] fp32
@@ -346,6 +347,7 @@ struct pdm_engine {
         const size_t npart = (d + LN_PART - 1) / LN_PART;
         w.stats_x = (float*)a.take(R1 * npart * 2 * 4);
         w.stats_mx = two_m ? (float*)a.take(R2 * npart * 2 * 4) : nullptr;
+        w.rstd = (float*)a.take(R * 4);
         w.skipx.resize(depth / 2);
         w.skipm.resize(two_m ? depth / 2 : 0);
         for (auto& sp : w.skipx) sp = a.take(R1 * d * act);
@@ -518,7 +520,8 @@ struct pdm_engine {
         {
             Scope sc(this, "gemm_qkv", s);
             GemmProblem g;
-            g.A1 = cur; g.K1 = D; g.W16 = w.qkv_f.w; g.bias = w.qkv_f.d; g.ln_stats = stats;
+            ln_rstd(stats, ws.rstd, R, D, s);
+            g.A1 = cur; g.K1 = D; g.W16 = w.qkv_f.w; g.bias = w.qkv_f.d; g.ln_rstd = ws.rstd;
             g.N = 3 * D; g.nb = 1; g.Lr = R; g.out2 = ws.qkv;
             gemm_tc_bf16(g, s);
         }
@@ -536,7 +539,8 @@ struct pdm_engine {
         {
             Scope sc(this, "gemm_fc1", s);
             GemmProblem g;
-            g.A1 = ws.h; g.K1 = D; g.W16 = w.fc1_f.w; g.bias = w.fc1_f.d; g.ln_stats = stats;
+            ln_rstd(stats, ws.rstd, R, D, s);
+            g.A1 = ws.h; g.K1 = D; g.W16 = w.fc1_f.w; g.bias = w.fc1_f.d; g.ln_rstd = ws.rstd;
             g.N = w.fc1.N; g.nb = 1; g.Lr = R; g.out2 = ws.u; g.gelu = true;
             gemm_tc_bf16(g, s);
         }
@@ -1119,7 +1123,7 @@ int pdm_debug_ln_chain(const float* A, const float* W1, const float* b1, const f
         cudaStream_t s = (cudaStream_t)stream;
         const int npart = (D + LN_PART - 1) / LN_PART;
         DevBuf x((size_t)M * D * 4), xb((size_t)M * D * 2), stats((size_t)M * npart * 8);
-        DevBuf wf((size_t)N * D * 2), d((size_t)N * 4), o16((size_t)M * N * 2);
+        DevBuf wf((size_t)N * D * 2), d((size_t)N * 4), o16((size_t)M * N * 2), rs((size_t)M * 4);
         PDM_CHECK_CUDA(cudaMemcpyAsync(x.p, resid, (size_t)M * D * 4, cudaMemcpyDeviceToDevice, s));
         if (A) {
             DevBuf a16((size_t)M * K1 * 2), w16((size_t)D * K1 * 2);
@@ -1136,7 +1140,8 @@ int pdm_debug_ln_chain(const float* A, const float* W1, const float* b1, const f
         fold_ln_weight(W2, b2, gamma, beta, (bf16*)wf.p, (float*)d.p, N, D, s);
         GemmProblem g;
         g.A1 = xb.p; g.K1 = D; g.W16 = (const bf16*)wf.p; g.bias = (const float*)d.p;
-        g.ln_stats = (const float*)stats.p; g.N = N; g.nb = 1; g.Lr = M; g.out2 = o16.p; g.gelu = gelu != 0;
+        ln_rstd((const float*)stats.p, (float*)rs.p, M, D, s);
+        g.ln_rstd = (const float*)rs.p; g.N = N; g.nb = 1; g.Lr = M; g.out2 = o16.p; g.gelu = gelu != 0;
         gemm_tc_bf16(g, s);
         time_kernel([&] { gemm_tc_bf16(g, s); }, iters, ms, s);
         bf16_to_f32_kernel<<<(unsigned)ceil_div_ll((long long)M * N, 256), 256, 0, s>>>((const bf16*)o16.p, out,

@@ -32,29 +32,40 @@ namespace {
 
 constexpr int BM = 128;  // accumulator rows per CTA
 constexpr int BN = 256, BK = 64;
-#ifndef PDM_GEMM_EPI_WARPS
-#define PDM_GEMM_EPI_WARPS 8
+#ifndef PDM_GEMM_LN_EPI_WARPS
+#define PDM_GEMM_LN_EPI_WARPS 16
 #endif
-constexpr int EPI_WARPS = PDM_GEMM_EPI_WARPS;  // 8 or 16: each covers one TMEM lane quarter x (BN / (EPI_WARPS / 4)) columns
-constexpr int WCOLS = 256 / (EPI_WARPS / 4);   // accumulator columns per epilogue warp
-constexpr int NBLK = WCOLS / 32;               // 32-column blocks per epilogue warp
-constexpr int THREADS = 64 + EPI_WARPS * 32;
 constexpr int A_BYTES = BM * BK * 2;
 constexpr int SCR_STRIDE = 36;  // 32-bit words per scratch row: 128 B payload + 16 B pad (16 B aligned, conflict-free)
-constexpr int LN_MAXPART = 8;   // LayerNorm-consuming form: K <= 8 * 128
-// + this warp's slice of the bias and LN column-sum vectors + a [32 lanes][LN_MAXPART] float2 landing zone for the
-// row sums of the NEXT tile (cp.async)
-constexpr int SCR_WORDS = 32 * SCR_STRIDE + 2 * WCOLS + 32 * LN_MAXPART * 2;
-static_assert(WCOLS == LN_PART, "the LayerNorm partial sums are per epilogue-warp column slice");
-constexpr int SCR_BYTES = SCR_WORDS * 4;
+enum { EPI_F32 = 0, EPI_PACK = 1, EPI_LN = 2, EPI_LN_GELU = 3, EPI_F32_EMIT = 4, EPI_LN_GELU_W16 = 5 };
+
+// Epilogue geometry per form.  Each epilogue warp covers one TMEM lane quarter x WCOLS accumulator columns.  The
+// fc1 form (LN + GELU, bf16 out) is latency-bound per warp (TMEM load -> FMA / tanh chain -> pack -> transpose, 94 registers):
+// for K <= 512 (MMA time per tile = 4096 clk) it runs 16 warps (4 per scheduler) on 64 columns each (_W16, measured -4 %;
+// for K >= 768 the MMAs dominate and the 4-stage ring that 16 warps force costs more than it gains).  The qkv form has too
+// little epilogue work to gain (+6.5 % with 16 warps), and the fp32 forms need ~150 registers: both stay at 8 warps.
+template <int EPI>
+struct Geo {
+    static constexpr bool LN = EPI == EPI_LN || EPI == EPI_LN_GELU || EPI == EPI_LN_GELU_W16;
+    static constexpr bool GELU = EPI == EPI_LN_GELU || EPI == EPI_LN_GELU_W16;
+    static constexpr int EW = EPI == EPI_LN_GELU_W16 ? PDM_GEMM_LN_EPI_WARPS : 8;
+    static constexpr int WCOLS = 256 / (EW / 4);  // accumulator columns per epilogue warp
+    static constexpr int NBLK = WCOLS / 32;       // 32-column blocks per epilogue warp
+    static constexpr int THREADS = 64 + EW * 32;
+    static constexpr int SCR_WORDS = 32 * SCR_STRIDE + WCOLS;  // transpose scratch + this warp's slice of the bias vector
+    static constexpr int SCR_BYTES = SCR_WORDS * 4;
+    static_assert(EW == 8 || EW == 16, "epilogue warps: 8 or 16");
+    static_assert(LN || WCOLS == LN_PART, "the LayerNorm partial sums are per (fp32-form) epilogue-warp column slice");
+};
 constexpr uint32_t TMEM_COLS = 512;
 
-template <int NCTA>
+template <int NCTA, int EPI>
 struct Cfg {
     static constexpr int B_BYTES = (BN / NCTA) * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = NCTA == 2 ? (EPI_WARPS > 8 ? 4 : 5) : 3;
-    static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + EPI_WARPS * SCR_BYTES + 256;
+    static constexpr int STAGES = NCTA == 2 ? (Geo<EPI>::EW > 8 ? 4 : 5) : 3;
+    static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + Geo<EPI>::EW * Geo<EPI>::SCR_BYTES + 256;
+    static_assert(SMEM_BYTES <= 232448, "dynamic shared memory budget");
 };
 
 struct TcParams {
@@ -75,16 +86,14 @@ struct TcParams {
     bf16* out2b;      // second bf16 copy, rows >= out2b_row0 of each batch only
     long long out2b_bs;
     int out2b_row0, out2b_mod;  // row filter: (row % out2b_mod if out2b_mod else row) >= out2b_row0
-    float* stats;     // [rows][npart][2] partial (sum, sum of squares) per WCOLS-column slice
+    float* stats;     // [rows][npart][2] partial (sum, sum of squares) per LN_PART-column slice
     long long stats_bs;
     float* statsb;
     long long statsb_bs;
-    int npart;        // ceil(N / WCOLS)
-    // deferred LayerNorm, consumer side (bf16 form): out = rstd * (acc - mean * ln_c[n]) + bias[n]
-    const float* ln_stats;
+    int npart;        // ceil(N / LN_PART)
+    // deferred LayerNorm, consumer side (bf16 form): out = rstd[row] * acc + bias[n]  (weight centred along K: no mean term)
+    const float* ln_rstd;
     long long ln_bs;
-    int ln_npart;     // ceil(K / WCOLS)
-    float ln_invK;
 };
 
 // GELU(erf) for the bf16 path (libs/timm.py:101 -> nn.GELU()).  x.Phi(x) = 0.5 x (1 + tanh(x (a + b x^2 + c x^4)))
@@ -160,13 +169,15 @@ __device__ __forceinline__ void release_accumulator(uint64_t* tempty_bar, uint32
 
 // EPI selects the epilogue at compile time (straight-line code per form: the epilogue is latency-bound with two warps per
 // scheduler, and runtime flags put a branch around every 8-column group, which kept the compiler from overlapping them)
-enum { EPI_F32 = 0, EPI_PACK = 1, EPI_LN = 2, EPI_LN_GELU = 3, EPI_F32_EMIT = 4 };  // _EMIT: + row sums / out2b (deferred LayerNorm producer)
+// (EPI_F32_EMIT = EPI_F32 + row sums / out2b: the deferred-LayerNorm producer)
 
 template <int NCTA, int EPI>
-__global__ void __cluster_dims__(NCTA, 1, 1) __launch_bounds__(THREADS, 1)
+__global__ void __cluster_dims__(NCTA, 1, 1) __launch_bounds__(Geo<EPI>::THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmB, const TcParams p) {
-    using C = Cfg<NCTA>;
+    using C = Cfg<NCTA, EPI>;
+    using G = Geo<EPI>;
+    constexpr int EPI_WARPS = G::EW, WCOLS = G::WCOLS, NBLK = G::NBLK, SCR_BYTES = G::SCR_BYTES;
     constexpr int STAGES = C::STAGES;
     constexpr int STAGE_BYTES = C::STAGE_BYTES;
     extern __shared__ uint8_t smem_raw[];
@@ -309,30 +320,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         const int half = ew >> 2;  // which WCOLS-column slice of the tile
         uint32_t* scr = reinterpret_cast<uint32_t*>(scr_base + ew * SCR_BYTES);
         float* sbias = reinterpret_cast<float*>(scr + 32 * SCR_STRIDE);  // [WCOLS]
-        float2* sstat = reinterpret_cast<float2*>(sbias + WCOLS) + lane * LN_MAXPART;  // this lane's row sums (cp.async)
         constexpr bool packed = EPI != EPI_F32 && EPI != EPI_F32_EMIT;
         constexpr bool EMIT = EPI == EPI_F32_EMIT;
-        constexpr bool LN = EPI == EPI_LN || EPI == EPI_LN_GELU;
-        // the partial row sums of a tile are fetched one tile ahead: read at the top of a tile they cost a full L2 / HBM
-        // round trip during which the finished accumulator sat unread (measured: qkv / fc1 27-30 % slower)
-        auto prefetch_stats = [&](int tile) {
+        constexpr bool LN = G::LN;
+        // deferred LayerNorm: 1 / std of the accumulator row this thread owns, fetched ONE TILE AHEAD into a register (read
+        // at the top of a tile it cost an L2 / HBM round trip during which the finished accumulator sat unread)
+        auto load_rstd = [&](int tile) -> float {
+            float r = 0.f;
             if (tile < p.total_tiles) {
                 const int mp = tile / p.ntn;
                 const int mt = NCTA * mp + (int)rank;
                 if (mt < p.n_mtiles) {
                     const int b = mt / p.tpb;
                     const int t = (mt - b * p.tpb) * BM + q * 32 + lane;
-                    if (t < p.Lr) {
-                        const float2* sp = reinterpret_cast<const float2*>(p.ln_stats) + ((long long)b * p.ln_bs + t) * p.ln_npart;
-                        const uint32_t dst = ptx::smem_u32(sstat);
-                        for (int i = 0; i < p.ln_npart; ++i)
-                            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 8 * i), "l"(sp + i) : "memory");
-                    }
+                    if (t < p.Lr) r = __ldg(p.ln_rstd + (long long)b * p.ln_bs + t);
                 }
             }
-            asm volatile("cp.async.commit_group;" ::: "memory");
+            return r;
         };
-        if (LN) prefetch_stats(unit_id);
+        float rstd_next = 0.f;
+        if (LN) rstd_next = load_rstd(unit_id);
         const int rsub = lane >> 3, c8 = lane & 7;
         int it = 0;
         for (int tile = unit_id; tile < p.total_tiles; tile += n_units, ++it) {
@@ -350,7 +357,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
             if constexpr (packed) {
                 // ---- bf16-only output: 2 chunks of 64 columns; bias/GELU in the row domain, pack, transpose ----
                 const bool has_bias = LN || p.bias != nullptr;
-                const bool gelu = LN ? (EPI == EPI_LN_GELU) : (p.gelu != 0);
+                const bool gelu = LN ? G::GELU : (p.gelu != 0);
                 if (has_bias) {
 #pragma unroll
                     for (int i = 0; i < NBLK; ++i) {
@@ -362,21 +369,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
                 // sums the producer of x left behind (read before the accumulator is waited for)
                 uint64_t rstd2 = 0;
                 if constexpr (LN) {
-                    float rstd = 0.f;
-                    asm volatile("cp.async.wait_group 0;" ::: "memory");
-                    if (trow0 + lane < lr_eff) {
-                        float a1 = 0.f, a2 = 0.f;
-                        for (int i = 0; i < p.ln_npart; ++i) {
-                            const float2 t = sstat[i];
-                            a1 += t.x;
-                            a2 += t.y;
-                        }
-                        const float mean = a1 * p.ln_invK;
-                        const float var = fmaxf(fmaf(-mean, mean, a2 * p.ln_invK), 0.f);
-                        rstd = rsqrtf(var + 1e-5f);
-                    }
-                    asm("mov.b64 %0, {%1, %1};" : "=l"(rstd2) : "f"(rstd));
-                    prefetch_stats(tile + n_units);
+                    asm("mov.b64 %0, {%1, %1};" : "=l"(rstd2) : "f"(rstd_next));
+                    rstd_next = load_rstd(tile + n_units);
                 }
                 __syncwarp();
                 ptx::mbar_wait(&tfull[as], aphase);
@@ -550,7 +544,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
                     }
                     const int r = c8 * 4 + rsub;
                     if (ncol0 < p.N && trow0 + r < lr_eff) {
-                        const int part = ncol0 / WCOLS;
+                        const int part = ncol0 / LN_PART;
                         reinterpret_cast<float2*>(p.stats)[((long long)b * p.stats_bs + trow0 + r) * p.npart + part] =
                             make_float2(w1, w2);
                         if (p.statsb)
@@ -634,11 +628,9 @@ void launch(const GemmProblem& g, cudaStream_t s) {
     p.stats_bs = g.stats_bs ? g.stats_bs : g.Lr;
     p.statsb = g.statsb;
     p.statsb_bs = g.statsb_bs ? g.statsb_bs : g.Lr;
-    p.npart = ceil_div(g.N, WCOLS);
-    p.ln_stats = g.ln_stats;
-    p.ln_bs = g.ln_stats_bs ? g.ln_stats_bs : g.Lr;
-    p.ln_npart = ceil_div(g.K1, WCOLS);
-    p.ln_invK = 1.f / (float)g.K1;
+    p.npart = ceil_div(g.N, LN_PART);
+    p.ln_rstd = g.ln_rstd;
+    p.ln_bs = g.ln_rstd_bs ? g.ln_rstd_bs : g.Lr;
     const CUtensorMap tmA1 = make_tmap_bf16_3d(g.A1, g.K1, g.Lr, g.nb, g.a1_bs ? g.a1_bs : g.Lr, BM, BK);
     const CUtensorMap tmA2 =
         g.A2 ? make_tmap_bf16_3d(g.A2, g.K2, g.Lr, g.nb, g.a2_bs ? g.a2_bs : g.Lr, BM, BK) : tmA1;
@@ -646,11 +638,11 @@ void launch(const GemmProblem& g, cudaStream_t s) {
     static bool attr_set = false;
     if (!attr_set) {
         PDM_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<NCTA, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            Cfg<NCTA>::SMEM_BYTES));
+                                            Cfg<NCTA, EPI>::SMEM_BYTES));
         attr_set = true;
     }
     const int units = std::max(1, std::min(p.total_tiles, num_sms() / NCTA));
-    gemm_tc_kernel<NCTA, EPI><<<NCTA * units, THREADS, Cfg<NCTA>::SMEM_BYTES, s>>>(tmA1, tmA2, tmB, p);
+    gemm_tc_kernel<NCTA, EPI><<<NCTA * units, Geo<EPI>::THREADS, Cfg<NCTA, EPI>::SMEM_BYTES, s>>>(tmA1, tmA2, tmB, p);
     check_launch("gemm_tc");
 }
 
@@ -694,25 +686,26 @@ void gemm_tc_bf16(const GemmProblem& g, cudaStream_t s) {
     PDM_REQUIRE(!g.out32b || g.out32, "gemm_tc: out32b needs out32");
     PDM_REQUIRE(!g.resid || (g.resid == g.out32 && (g.resid_bs ? g.resid_bs : g.Lr) == (g.out32_bs ? g.out32_bs : g.Lr)),
                 "gemm_tc: the residual must be the fp32 output (in-place accumulate)");
-    PDM_REQUIRE(!g.ln_stats || g.K1 <= LN_MAXPART * WCOLS, "gemm_tc: the LayerNorm-consuming form supports K <= 1024");
-    PDM_REQUIRE(!g.ln_stats || (g.bias && !g.A2 && !g.out32 && g.N % 8 == 0),
+    PDM_REQUIRE(!g.ln_rstd || (g.bias && !g.A2 && !g.out32 && g.N % 8 == 0),
                 "gemm_tc: the LayerNorm-consuming form needs the folded bias, a single A and a bf16-only output");
     PDM_REQUIRE(g.out32 || g.N % 8 == 0, "gemm_tc: the bf16-only output form needs N % 8 == 0");
     PDM_REQUIRE((!g.stats && !g.statsb && !g.out2b) || g.out32, "gemm_tc: row sums / out2b belong to the fp32-output form");
     PDM_REQUIRE(!g.statsb || g.stats, "gemm_tc: statsb needs stats");
     static const bool one_cta = getenv("PDM_GEMM_1CTA") != nullptr;
-    const int epi = g.out32 ? ((g.stats || g.out2b) ? EPI_F32_EMIT : EPI_F32) : (g.ln_stats ? (g.gelu ? EPI_LN_GELU : EPI_LN) : EPI_PACK);
+    const int epi = g.out32 ? ((g.stats || g.out2b) ? EPI_F32_EMIT : EPI_F32) : (g.ln_rstd ? (g.gelu ? (g.K1 <= 512 ? EPI_LN_GELU_W16 : EPI_LN_GELU) : EPI_LN) : EPI_PACK);
     if (one_cta) {
         if (epi == EPI_F32) launch<1, EPI_F32>(g, s);
         else if (epi == EPI_F32_EMIT) launch<1, EPI_F32_EMIT>(g, s);
         else if (epi == EPI_PACK) launch<1, EPI_PACK>(g, s);
         else if (epi == EPI_LN) launch<1, EPI_LN>(g, s);
+        else if (epi == EPI_LN_GELU_W16) launch<1, EPI_LN_GELU_W16>(g, s);
         else launch<1, EPI_LN_GELU>(g, s);
     } else {
         if (epi == EPI_F32) launch<2, EPI_F32>(g, s);
         else if (epi == EPI_F32_EMIT) launch<2, EPI_F32_EMIT>(g, s);
         else if (epi == EPI_PACK) launch<2, EPI_PACK>(g, s);
         else if (epi == EPI_LN) launch<2, EPI_LN>(g, s);
+        else if (epi == EPI_LN_GELU_W16) launch<2, EPI_LN_GELU_W16>(g, s);
         else launch<2, EPI_LN_GELU>(g, s);
     }
 }
