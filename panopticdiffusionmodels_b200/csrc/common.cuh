@@ -115,6 +115,8 @@ struct EmbedArgs {
     float t_scalar;
     const float* freqs;    // [D/2]
     const float* ctxtok;   // [nb, T, D] (bias already added)
+    const float* wT_img;   // [C*p*p, D]  patch_embed.proj.weight transposed (engine builds it at finalize)
+    const float* wT_msk;   // [Cm*p*p, D]
     const float* w_img;    // [D, C*p*p]
     const float* b_img;
     const float* w_msk;    // [D, Cm*p*p]
@@ -128,6 +130,7 @@ struct EmbedArgs {
     int C, Cm, S, p, D, T;
 };
 void embed_tokens(const EmbedArgs& a, cudaStream_t s);
+void transpose_f32(const float* in, float* out, int R, int C, cudaStream_t s);  // [R, C] -> [C, R]
 
 struct HeadArgs {
     const float* x;       // [nb, Lx, D] image tokens at offset x_off

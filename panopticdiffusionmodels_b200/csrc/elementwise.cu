@@ -277,62 +277,101 @@ __global__ void __launch_bounds__(128) embed_extras_kernel(EmbedArgs a) {
     }
 }
 
-// Kernel B: patch embedding (Conv2d k = s = p == per-patch dot product, weight (D, C, p, p)) for the image and
-// the mask stream.  One block = 32 patches of one stream of one row; each thread owns output channels
-// d = tid, tid + 256, ... with its weight row in registers; patch pixels are broadcast from shared memory.
-// HBM-bound on the [tokens, D] fp32 write.
-constexpr int EMB_TOK = 32;
+// Kernel B: patch embedding (Conv2d k = s = p == per-patch dot product, weight (D, C, p, p)) for the image and the
+// mask stream as a small register-tiled GEMM.  One block = 64 patches x 128 channels of one stream of one sample; a warp
+// owns 8 patches, a lane 4 consecutive channels (float4 row-contiguous stores of 512 B per warp).  Weights arrive
+// pre-transposed ([C*p*p, D], built once at finalize) so the shared-memory tile is filled with coalesced float4 loads;
+// patch pixels are broadcast reads.  128 FMAs per 12 shared loads: HBM-bound on the [tokens, D] fp32 write.
+constexpr int EMB_TOK = 64, EMB_DT = 128;
 template <int KK>
 __global__ void __launch_bounds__(256) embed_patch_kernel(EmbedArgs a) {
     __shared__ __align__(16) float patch[EMB_TOK][KK];
+    __shared__ __align__(16) float wts[KK][EMB_DT];
     const int g = a.S / a.p;
     const int P = g * g;
     const int ext = 1 + a.T;
-    const int tile = blockIdx.x, is_mask = blockIdx.y, b = blockIdx.z;
+    const int nstream = a.mask ? 2 : 1;
+    const int tile = blockIdx.x, d0 = blockIdx.y * EMB_DT;
+    const int is_mask = blockIdx.z % nstream, b = blockIdx.z / nstream;
     const int bi = b % a.Bx;
     const int C = is_mask ? a.Cm : a.C;
     const int pp = a.p * a.p;
+    const int kk = C * pp;
     const float* src = (is_mask ? a.mask : a.img) + (long long)bi * C * a.S * a.S;
     for (int i = threadIdx.x; i < EMB_TOK * KK; i += blockDim.x) {
         const int t = i / KK, k = i % KK;
         const int pidx = tile * EMB_TOK + t;
         float v = 0.f;
-        if (pidx < P && k < C * pp) {
+        if (pidx < P && k < kk) {
             const int ph = pidx / g, pw = pidx % g;
             const int c = k / pp, r = k % pp;
             v = src[((long long)c * a.S + ph * a.p + r / a.p) * a.S + pw * a.p + r % a.p];
         }
         patch[t][k] = v;
     }
+    const float* wT = is_mask ? a.wT_msk : a.wT_img;  // [kk, D]
+    for (int i = threadIdx.x; i < KK * (EMB_DT / 4); i += blockDim.x) {
+        const int k = i / (EMB_DT / 4), c4 = i % (EMB_DT / 4);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k < kk && d0 + c4 * 4 < a.D) v = __ldg(reinterpret_cast<const float4*>(wT + (long long)k * a.D + d0) + c4);
+        *reinterpret_cast<float4*>(&wts[k][c4 * 4]) = v;
+    }
     __syncthreads();
-    const float* w = is_mask ? a.w_msk : a.w_img;
-    const float* bias = is_mask ? a.b_msk : a.b_img;
-    const int kk = C * pp;
-    for (int d = threadIdx.x; d < a.D; d += blockDim.x) {
-        float wr[KK];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int t0 = warp * 8;
+    float4 acc[8];
 #pragma unroll
-        for (int k = 0; k < KK; ++k) wr[k] = k < kk ? __ldg(w + (long long)d * kk + k) : 0.f;
-        const float bd = bias[d];
-        for (int t = 0; t < EMB_TOK; ++t) {
-            const int pidx = tile * EMB_TOK + t;
-            if (pidx >= P) break;
-            float acc = 0.f;
+    for (int t = 0; t < 8; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int k = 0; k < KK; k += 4) {
-                const float4 pv = *reinterpret_cast<const float4*>(&patch[t][k]);
-                acc = fmaf(wr[k], pv.x, acc);
-                acc = fmaf(wr[k + 1], pv.y, acc);
-                acc = fmaf(wr[k + 2], pv.z, acc);
-                acc = fmaf(wr[k + 3], pv.w, acc);
-            }
-            if (is_mask) {
-                a.out_m[((long long)b * a.Lm + a.m_off + pidx) * a.D + d] = acc + bd + a.pos_m[(long long)pidx * a.D + d];
-            } else {
-                const int tok = ext + pidx;
-                a.out_x[((long long)b * a.Lx + tok) * a.D + d] = acc + bd + a.pos[(long long)tok * a.D + d];
+    for (int k4 = 0; k4 < KK / 4; ++k4) {
+        float4 pk[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) pk[t] = *reinterpret_cast<const float4*>(&patch[t0 + t][k4 * 4]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float4 w4 = *reinterpret_cast<const float4*>(&wts[k4 * 4 + j][lane * 4]);
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                const float pv = j == 0 ? pk[t].x : (j == 1 ? pk[t].y : (j == 2 ? pk[t].z : pk[t].w));
+                acc[t].x = fmaf(pv, w4.x, acc[t].x);
+                acc[t].y = fmaf(pv, w4.y, acc[t].y);
+                acc[t].z = fmaf(pv, w4.z, acc[t].z);
+                acc[t].w = fmaf(pv, w4.w, acc[t].w);
             }
         }
     }
+    const int d = d0 + lane * 4;
+    if (d >= a.D) return;
+    const float4 b4 = __ldg(reinterpret_cast<const float4*>((is_mask ? a.b_msk : a.b_img) + d));
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        const int pidx = tile * EMB_TOK + t0 + t;
+        if (pidx >= P) break;
+        const float* pe;
+        float* o;
+        if (is_mask) {
+            pe = a.pos_m + (long long)pidx * a.D + d;
+            o = a.out_m + ((long long)b * a.Lm + a.m_off + pidx) * a.D + d;
+        } else {
+            pe = a.pos + (long long)(ext + pidx) * a.D + d;
+            o = a.out_x + ((long long)b * a.Lx + ext + pidx) * a.D + d;
+        }
+        const float4 q = __ldg(reinterpret_cast<const float4*>(pe));
+        // (acc + bias) + pos: the reference adds the conv bias first, then the positional embedding
+        *reinterpret_cast<float4*>(o) = make_float4((acc[t].x + b4.x) + q.x, (acc[t].y + b4.y) + q.y,
+                                                    (acc[t].z + b4.z) + q.z, (acc[t].w + b4.w) + q.w);
+    }
+}
+
+__global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int R, int Cc) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)R * Cc) return;
+    const int r = (int)(i / Cc), c = (int)(i % Cc);
+    out[(long long)c * R + r] = in[i];
+}
+void transpose_f32(const float* in, float* out, int R, int Cc, cudaStream_t s) {
+    transpose_kernel<<<(unsigned)ceil_div_ll((long long)R * Cc, 256), 256, 0, s>>>(in, out, R, Cc);
+    check_launch("transpose");
 }
 
 void embed_tokens(const EmbedArgs& a, cudaStream_t s) {
@@ -343,7 +382,8 @@ void embed_tokens(const EmbedArgs& a, cudaStream_t s) {
     const int P = g * g;
     embed_extras_kernel<<<dim3(1 + a.T, a.nb), 128, 0, s>>>(a);
     check_launch("embed_extras");
-    dim3 grid(ceil_div(P, EMB_TOK), a.mask ? 2 : 1, a.nb);
+    PDM_REQUIRE(a.wT_img && (!a.mask || a.wT_msk), "embed: transposed patch weights missing");
+    dim3 grid(ceil_div(P, EMB_TOK), ceil_div(a.D, EMB_DT), a.nb * (a.mask ? 2 : 1));
     if (kmax <= 16)
         embed_patch_kernel<16><<<grid, 256, 0, s>>>(a);
     else if (kmax <= 32)
@@ -358,56 +398,64 @@ void embed_tokens(const EmbedArgs& a, cudaStream_t s) {
 // unpatchify -> 3x3 conv (+ tanh on the mask).
 // Kernel 1: one warp per (row, patch, stream); kernel 2: one thread per output pixel.
 // ----------------------------------------------------------------------------------------------
+// One warp = HEAD_T consecutive patches of one stream of one sample.  The (normalised) token rows live in registers
+// (lane owns float4 chunks lane + 32 i); every decoder weight row is read once per HEAD_T tokens, and the 32-lane partial
+// sums of 8 outputs are combined with a transposing butterfly (4 + 2 + 1 + 2 shuffles per token instead of 8 x 5).
+constexpr int HEAD_T = 4;
 template <int NV>
 __global__ void __launch_bounds__(256) head_token_kernel(HeadArgs a) {
     const int g = a.S / a.p;
     const int P = g * g;
+    const int gpr = (P + HEAD_T - 1) / HEAD_T;  // token groups per (stream, sample)
     const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     const int nstream = a.m ? 2 : 1;
-    if (warp >= a.nb * P * nstream) return;
-    const int stream = warp / (a.nb * P);
-    const int rem = warp - stream * a.nb * P;
-    const int b = rem / P, pidx = rem % P;
-    const float* row = stream == 0 ? a.x + ((long long)b * a.Lx + a.x_off + pidx) * a.D
-                                   : a.m + ((long long)b * a.Lm + a.m_off + pidx) * a.D;
+    if (warp >= a.nb * gpr * nstream) return;
+    const int stream = warp / (a.nb * gpr);
+    const int rem = warp - stream * a.nb * gpr;
+    const int b = rem / gpr, p0 = (rem % gpr) * HEAD_T;
     const bool do_ln = stream == 0 || a.ln_m;
     const int D = a.D;
-    // the (optionally normalised) token row lives in registers: lane owns float4 chunks lane + 32 i
-    float4 v[NV];
-    float sum = 0.f;
+    float4 v[HEAD_T][NV];
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-        const int c = lane + 32 * i;
-        v[i] = c * 4 < D ? __ldg(reinterpret_cast<const float4*>(row) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-        sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-    }
-    if (do_ln) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        const float mean = sum / (float)D;
-        float sq = 0.f;
+    for (int t = 0; t < HEAD_T; ++t) {
+        const int pidx = min(p0 + t, P - 1);  // a ragged last group recomputes the last patch (its store is skipped)
+        const float* row = stream == 0 ? a.x + ((long long)b * a.Lx + a.x_off + pidx) * D
+                                       : a.m + ((long long)b * a.Lm + a.m_off + pidx) * D;
+        float sum = 0.f;
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
             const int c = lane + 32 * i;
-            if (c * 4 < D) {
-                const float e0 = v[i].x - mean, e1 = v[i].y - mean, e2 = v[i].z - mean, e3 = v[i].w - mean;
-                sq += (e0 * e0 + e1 * e1) + (e2 * e2 + e3 * e3);
-            }
+            v[t][i] = c * 4 < D ? __ldg(reinterpret_cast<const float4*>(row) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            sum += (v[t][i].x + v[t][i].y) + (v[t][i].z + v[t][i].w);
         }
+        if (do_ln) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-        const float rstd = rsqrtf(sq / (float)D + 1e-5f);
+            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            const float mean = sum / (float)D;
+            float sq = 0.f;
 #pragma unroll
-        for (int i = 0; i < NV; ++i) {
-            const int c = lane + 32 * i;
-            if (c * 4 < D) {
-                const float4 w4 = __ldg(reinterpret_cast<const float4*>(a.ln_w) + c);
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.ln_b) + c);
-                v[i].x = (v[i].x - mean) * rstd * w4.x + b4.x;
-                v[i].y = (v[i].y - mean) * rstd * w4.y + b4.y;
-                v[i].z = (v[i].z - mean) * rstd * w4.z + b4.z;
-                v[i].w = (v[i].w - mean) * rstd * w4.w + b4.w;
+            for (int i = 0; i < NV; ++i) {
+                const int c = lane + 32 * i;
+                if (c * 4 < D) {
+                    const float e0 = v[t][i].x - mean, e1 = v[t][i].y - mean, e2 = v[t][i].z - mean, e3 = v[t][i].w - mean;
+                    sq += (e0 * e0 + e1 * e1) + (e2 * e2 + e3 * e3);
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+            const float rstd = rsqrtf(sq / (float)D + 1e-5f);
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                const int c = lane + 32 * i;
+                if (c * 4 < D) {
+                    const float4 w4 = __ldg(reinterpret_cast<const float4*>(a.ln_w) + c);
+                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.ln_b) + c);
+                    v[t][i].x = (v[t][i].x - mean) * rstd * w4.x + b4.x;
+                    v[t][i].y = (v[t][i].y - mean) * rstd * w4.y + b4.y;
+                    v[t][i].z = (v[t][i].z - mean) * rstd * w4.z + b4.z;
+                    v[t][i].w = (v[t][i].w - mean) * rstd * w4.w + b4.w;
+                }
             }
         }
     }
@@ -416,32 +464,53 @@ __global__ void __launch_bounds__(256) head_token_kernel(HeadArgs a) {
     const float* W = stream == 0 ? a.w_dec : a.w_decm;
     const float* bias = stream == 0 ? a.b_dec : a.b_decm;
     float* dst = (stream == 0 ? a.tmp_img : a.tmp_msk) + (long long)b * C * a.S * a.S;
-    const int ph = pidx / g, pw = pidx % g;
-    float mine = 0.f;  // lane o keeps output o
-    for (int o = 0; o < nout; ++o) {
-        const float4* wr = reinterpret_cast<const float4*>(W + (long long)o * D);
-        float acc = 0.f;
+    for (int o0 = 0; o0 < nout; o0 += 8) {
+        float acc[HEAD_T][8];
 #pragma unroll
-        for (int i = 0; i < NV; ++i) {
-            const int c = lane + 32 * i;
-            if (c * 4 < D) {
-                const float4 w4 = __ldg(wr + c);
-                acc = fmaf(v[i].x, w4.x, acc);
-                acc = fmaf(v[i].y, w4.y, acc);
-                acc = fmaf(v[i].z, w4.z, acc);
-                acc = fmaf(v[i].w, w4.w, acc);
+        for (int j = 0; j < 8; ++j) {
+            const float4* wr = reinterpret_cast<const float4*>(W + (long long)min(o0 + j, nout - 1) * D);
+#pragma unroll
+            for (int t = 0; t < HEAD_T; ++t) acc[t][j] = 0.f;
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                const int c = lane + 32 * i;
+                if (c * 4 < D) {
+                    const float4 w4 = __ldg(wr + c);
+#pragma unroll
+                    for (int t = 0; t < HEAD_T; ++t) {
+                        acc[t][j] = fmaf(v[t][i].x, w4.x, acc[t][j]);
+                        acc[t][j] = fmaf(v[t][i].y, w4.y, acc[t][j]);
+                        acc[t][j] = fmaf(v[t][i].z, w4.z, acc[t][j]);
+                        acc[t][j] = fmaf(v[t][i].w, w4.w, acc[t][j]);
+                    }
+                }
             }
         }
+        // transposing butterfly over lane bits 2..0: lane l ends with output o0 + (l & 7) summed over its 8-lane group,
+        // then two plain exchanges over bits 3 and 4 complete the sum (every lane of a residue class holds the total)
+        const int oo = o0 + (lane & 7);
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-        if ((o & 31) == lane) mine = acc;
-        if ((o & 31) == 31 || o == nout - 1) {
-            const int oo = (o & ~31) + lane;
-            if (oo <= o) {
+        for (int t = 0; t < HEAD_T; ++t) {
+#pragma unroll
+            for (int off = 4; off >= 1; off >>= 1) {
+                const bool up = (lane & off) != 0;
+#pragma unroll
+                for (int i = 0; i < off; ++i) {
+                    const float send = up ? acc[t][i] : acc[t][i + off];
+                    const float recv = __shfl_xor_sync(0xffffffffu, send, off);
+                    acc[t][i] = (up ? acc[t][i + off] : acc[t][i]) + recv;
+                }
+            }
+            float r = acc[t][0];
+            r += __shfl_xor_sync(0xffffffffu, r, 8);
+            r += __shfl_xor_sync(0xffffffffu, r, 16);
+            const int pidx = p0 + t;
+            if (lane < 8 && oo < nout && pidx < P) {
                 // feature oo = (p1 * p + p2) * C + c  ->  pixel (ph*p + p1, pw*p + p2), channel c
+                const int ph = pidx / g, pw = pidx % g;
                 const int c = oo % C, pq = oo / C;
                 const int p1 = pq / a.p, p2 = pq % a.p;
-                dst[((long long)c * a.S + ph * a.p + p1) * a.S + pw * a.p + p2] = mine + bias[oo];
+                dst[((long long)c * a.S + ph * a.p + p1) * a.S + pw * a.p + p2] = r + bias[oo];
             }
         }
     }
@@ -479,16 +548,15 @@ __global__ void __launch_bounds__(256) conv3x3_kernel(const float* __restrict__ 
 void head_decode(const HeadArgs& a, cudaStream_t s) {
     const int g = a.S / a.p;
     const int P = g * g;
-    const int nwarps = a.nb * P * (a.m ? 2 : 1);
-    PDM_REQUIRE(a.D % 4 == 0 && a.D <= 2048, "head: D must be a multiple of 4 and <= 2048");
+    const int nwarps = a.nb * ceil_div(P, HEAD_T) * (a.m ? 2 : 1);
+    PDM_REQUIRE(a.D % 4 == 0 && a.D <= 1024, "head: D must be a multiple of 4 and <= 1024");
     const int nv = ceil_div(a.D, 128);
     const int hgrid = ceil_div(nwarps, 8);
     if (nv <= 1) head_token_kernel<1><<<hgrid, 256, 0, s>>>(a);
     else if (nv <= 2) head_token_kernel<2><<<hgrid, 256, 0, s>>>(a);
     else if (nv <= 4) head_token_kernel<4><<<hgrid, 256, 0, s>>>(a);
     else if (nv <= 6) head_token_kernel<6><<<hgrid, 256, 0, s>>>(a);
-    else if (nv <= 8) head_token_kernel<8><<<hgrid, 256, 0, s>>>(a);
-    else head_token_kernel<16><<<hgrid, 256, 0, s>>>(a);
+    else head_token_kernel<8><<<hgrid, 256, 0, s>>>(a);
     check_launch("head_token");
     {
         const long long total = (long long)a.nb * a.C * a.S * a.S;

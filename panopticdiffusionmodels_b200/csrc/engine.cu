@@ -122,6 +122,7 @@ struct pdm_engine {
     std::map<std::string, FoldW> folds;  // keyed by "<block prefix>qkv" / "<block prefix>fc1"; allocated once (graphs bake pointers)
     LinearW ctx_lin;
     float* freqs = nullptr;
+    float *wT_img = nullptr, *wT_msk = nullptr;  // patch-embed weights transposed to [C*p*p, D] (embed kernel operand)
     std::vector<std::unique_ptr<Workspace>> spaces;
     std::vector<GraphEntry> graphs;
     bool profiling = false;
@@ -136,6 +137,8 @@ struct pdm_engine {
             if (kv.second.d16) cudaFree(kv.second.d16);
         }
         if (freqs) cudaFree(freqs);
+        if (wT_img) cudaFree(wT_img);
+        if (wT_msk) cudaFree(wT_msk);
         for (auto& kv : folds) {
             if (kv.second.w) cudaFree(kv.second.w);
             if (kv.second.d) cudaFree(kv.second.d);
@@ -319,6 +322,16 @@ struct pdm_engine {
             if (two) {
                 fold_block("in_blocks_mask." + std::to_string(i) + ".", in_bm[i], s);
                 fold_block("out_blocks_mask." + std::to_string(i) + ".", out_bm[i], s);
+            }
+        }
+        {
+            const int kk = C * p * p;
+            if (!wT_img) PDM_CHECK_CUDA(cudaMalloc(&wT_img, (size_t)kk * D * sizeof(float)));
+            transpose_f32(params.at("patch_embed.proj.weight").d32, wT_img, D, kk, s);
+            if (cfg.enable_panoptic) {
+                const int kkm = Cm * p * p;
+                if (!wT_msk) PDM_CHECK_CUDA(cudaMalloc(&wT_msk, (size_t)kkm * D * sizeof(float)));
+                transpose_f32(params.at("mask_embed.proj.weight").d32, wT_msk, D, kkm, s);
             }
         }
         fold_block("mid_block.", mid_b, s);
@@ -674,6 +687,7 @@ struct pdm_engine {
             EmbedArgs a;
             a.img = img; a.mask = mask; a.Bx = Bx; a.nb = nb; a.t_dev = t_dev; a.t_scalar = t_scalar;
             a.freqs = freqs; a.ctxtok = ws.ctxtok;
+            a.wT_img = wT_img; a.wT_msk = with_mask ? wT_msk : nullptr;
             a.w_img = params.at("patch_embed.proj.weight").d32;
             a.b_img = params.at("patch_embed.proj.bias").d32;
             a.w_msk = with_mask ? params.at("mask_embed.proj.weight").d32 : nullptr;
