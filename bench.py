@@ -72,12 +72,14 @@ def peaks():
 
 
 def gemm_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
-    `ncu --set full` capture (profiles/r01_gemm_ncu_summary.md); None when no capture is committed."""
-    p = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
-    if not os.path.exists(p):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the newest committed
+    `ncu --set full` capture (profiles/*_gemm_traffic.json, written by tools/summarise_profiles.py); None when no
+    capture is committed."""
+    import glob
+    cands = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_gemm_traffic.json")))
+    if not cands:
         return None
-    return json.load(open(p)).get("dram_bytes_per_launch_mean")
+    return json.load(open(cands[-1])).get("dram_bytes_per_launch_mean")
 
 
 class ClockSampler(threading.Thread):
