@@ -87,6 +87,14 @@ int pdm_workspace_bytes(pdm_handle h, int32_t n, int32_t precision, size_t* byte
 int pdm_nnet_forward(pdm_handle h, const float* x, const float* t, const float* ctx, const float* mask,
                      float* out_noise, float* out_mask, int32_t n, int32_t precision, void* stream);
 
+/* pdm_nnet_forward with option flags.  PDM_FWD_GROUND_TRUTH = the reference's `use_ground_truth=True` evaluation
+ * (libs/uvit_t2i.py:380, 486-496): the noise is decoded from image feature + mask feature (mask tokens normalised only in
+ * the single-stream topology), the mask decoder is skipped and out_mask receives the mask that was passed in.  This is
+ * the evaluation the second phase of DPM_Solver.sample(use_twophases=True) runs (dpm_solver_pp.py:1071-1075). */
+#define PDM_FWD_GROUND_TRUTH 1
+int pdm_nnet_forward_ex(pdm_handle h, const float* x, const float* t, const float* ctx, const float* mask, float* out_noise,
+                        float* out_mask, int32_t n, int32_t precision, int32_t flags, void* stream);
+
 /* replaces: cfg_nnet's guidance combine (train_t2i_discrete.py:429-431) + DPM_Solver.model_fn's
  * eps->x0 (dpm_solver_pp.py:316) + one singlestep linear update (dpm_solver_pp.py:444-456, 529-555,
  * 724-764), fused in ONE elementwise kernel.  `coef` is a HOST pointer to one plan record.

@@ -21,6 +21,7 @@ Reference lines followed (``/root/reference``):
   1S / 2S / 3S updates             dpm_solver_pp.py:432-457, 524-557, 713-766
   2M / 3M updates                  dpm_solver_pp.py:602-677
   sample(method='fast')            dpm_solver_pp.py:1018-1044
+  sample(method='singlestep'), two phases / ground truth   dpm_solver_pp.py:1045-1078; libs/uvit_t2i.py:486-496
   cfg_nnet                         train_t2i_discrete.py:387-439
   int2bits / bits2int              utils.py:475-518
 """
@@ -106,10 +107,12 @@ class Solver:
 
     def __init__(self, model: ModelFn, sched: Schedule, trace: Optional[list] = None):
         self.model, self.ns, self.trace = model, sched, trace
+        self.gt = False        # use_ground_truth handed to the model (dpm_solver_pp.py:310-314)
+        self.mask_opt = True   # enable_mask_opt: co-evolve the mask (False: pass it through, :459-461, :592-599, :823-829)
 
     def _x0(self, x, t, mask):
         a, s = self.ns.alpha(t), self.ns.sigma(t)
-        eps, pm = self.model(x, t, mask)
+        eps, pm = self.model(x, t, mask, gt=True) if self.gt else self.model(x, t, mask)
         x0 = (x - s * eps) / a
         if self.trace is not None:
             self.trace.append(dict(t=float(t), x_in=x.clone(), m_in=None if mask is None else mask.clone(),
@@ -123,6 +126,8 @@ class Solver:
         phi_1 = (torch.exp(-h) - 1.0) / (-1.0)
         X, P = self._x0(x, s, mask)
         x_t = (sig_t / sig_s) * x + (a_t * phi_1) * X
+        if not self.mask_opt:
+            return x_t, P, P
         m_t = None if mask is None else (sig_t / sig_s) * mask + (a_t * phi_1) * P
         return x_t, P, m_t
 
@@ -138,8 +143,12 @@ class Solver:
         X, P = self._x0(x, s, mask)
         x_s1 = (sig_s1 / sig_s) * x - (a_s1 * phi_11) * X
         m_s1 = None if mask is None else (sig_s1 / sig_s) * mask + (a_s1 * phi_11) * P  # sign quirk (:536-539)
+        if not self.mask_opt:
+            m_s1 = mask
         X1, P1 = self._x0(x_s1, s1, m_s1)
         x_t = (sig_t / sig_s) * x - (a_t * phi_1) * X - (0.5 / r1) * (a_t * phi_1) * (X1 - X)
+        if not self.mask_opt:
+            return x_t, P, P
         m_t = None
         if mask is not None:
             m_t = (sig_t / sig_s) * mask - (a_t * phi_1) * P - (0.5 / r1) * (a_t * phi_1) * (P1 - P)
@@ -161,13 +170,19 @@ class Solver:
         X, P = self._x0(x, s, mask)
         x_s1 = (sig_s1 / sig_s) * x - (a_s1 * phi_11) * X
         m_s1 = None if mask is None else (sig_s1 / sig_s) * mask + (a_s1 * phi_11) * P  # sign quirk (:730-733)
+        if not self.mask_opt:
+            m_s1 = mask
         X1, P1 = self._x0(x_s1, s1, m_s1)
         x_s2 = (sig_s2 / sig_s) * x - (a_s2 * phi_12) * X + r2 / r1 * (a_s2 * phi_22) * (X1 - X)
         m_s2 = None
         if mask is not None:
             m_s2 = (sig_s2 / sig_s) * mask - (a_s2 * phi_12) * P + r2 / r1 * (a_s2 * phi_22) * (P1 - P)
+        if not self.mask_opt:
+            m_s2 = mask
         X2, P2 = self._x0(x_s2, s2, m_s2)
         x_t = (sig_t / sig_s) * x - (a_t * phi_1) * X + (1.0 / r2) * (a_t * phi_2) * (X2 - X)
+        if not self.mask_opt:
+            return x_t, P, P
         m_t = None
         if mask is not None:
             m_t = (sig_t / sig_s) * mask - (a_t * phi_1) * P + (1.0 / r2) * (a_t * phi_2) * (P2 - P)
@@ -191,6 +206,34 @@ class Solver:
             else:
                 x, pred_mask, mask_t = self.third(x, s, t, r1, r2, mask_t)
             i += o
+        return x, pred_mask
+
+    def sample_singlestep(self, x, mask, steps, order=3, eps=1e-3, T=1.0, two_phases=False):
+        """method='singlestep' (dpm_solver_pp.py:1045-1078): steps // order updates of one fixed order with the default
+        r1 / r2 on a uniform time grid; with ``two_phases`` the same grid is walked a second time from the phase-one image with
+        the phase-one mask held fixed and handed to the network as ground truth (enable_mask_opt=False,
+        use_ground_truth=True); the returned pred_mask is phase one's."""
+        n = steps // order
+        ts = torch.linspace(T, eps, n + 1)
+
+        def walk(x, mask_t):
+            pred_mask = mask_t
+            for i in range(n):
+                s, t = ts[i], ts[i + 1]
+                if order == 1:
+                    x, pred_mask, mask_t = self.first(x, s, t, mask_t)
+                elif order == 2:
+                    x, pred_mask, mask_t = self.second(x, s, t, 0.5, mask_t)
+                else:
+                    x, pred_mask, mask_t = self.third(x, s, t, 1.0 / 3.0, 2.0 / 3.0, mask_t)
+            return x, pred_mask, mask_t
+
+        x, pred_mask, mask_t = walk(x, mask)
+        if two_phases:
+            keep = (self.gt, self.mask_opt)
+            self.gt, self.mask_opt = True, False
+            x, _, _ = walk(x, mask_t)
+            self.gt, self.mask_opt = keep
         return x, pred_mask
 
     # --- multistep pure updates (dpm_solver_pp.py:602-677), data prediction, 'dpm_solver' ---
@@ -229,7 +272,7 @@ def cfg_model(sd, cfg, context, empty_context, scale, dtype=F32, n_time=1000) ->
     """train_t2i_discrete.py:387-439 + :506-516: two forwards (cond / empty context),
     CFG on both eps and the mask prediction, model time = 1000 * t."""
 
-    def fn(x, t_cont, mask):
+    def fn(x, t_cont, mask, gt=False):
         B = x.shape[0]
         t = (torch.ones(B) * t_cont) * n_time
         ec = empty_context.unsqueeze(0).expand(B, -1, -1)
@@ -237,8 +280,8 @@ def cfg_model(sd, cfg, context, empty_context, scale, dtype=F32, n_time=1000) ->
             c = uvit_oracle.uvit_forward(sd, cfg, x, t, context, None, dtype).float()
             u = uvit_oracle.uvit_forward(sd, cfg, x, t, ec, None, dtype).float()
             return c + scale * (c - u), None
-        c, pc = uvit_oracle.uvit_forward(sd, cfg, x, t, context, mask, dtype)
-        u, pu = uvit_oracle.uvit_forward(sd, cfg, x, t, ec, mask, dtype)
+        c, pc = uvit_oracle.uvit_forward(sd, cfg, x, t, context, mask, dtype, use_ground_truth=gt)
+        u, pu = uvit_oracle.uvit_forward(sd, cfg, x, t, ec, mask, dtype, use_ground_truth=gt)
         c, pc, u, pu = c.float(), pc.float(), u.float(), pu.float()
         pm = pc + scale * (pc - pu)
         return c + scale * (c - u), pm

@@ -97,7 +97,7 @@ def _block(x, sd, pre, num_heads, skip=None):
 
 def uvit_forward(sd: Dict[str, torch.Tensor], cfg: dict, x: torch.Tensor, timesteps: torch.Tensor,
                  context: torch.Tensor, mask_token: Optional[torch.Tensor] = None,
-                 dtype: torch.dtype = torch.float32):
+                 dtype: torch.dtype = torch.float32, use_ground_truth: bool = False):
     """Evaluate the network.  ``cfg`` holds the reference ctor kwargs
     (img_size, patch_size, in_chans, embed_dim, depth, num_heads, num_clip_token,
     num_panoptic_class, separate).  Returns ``noise`` or ``(noise, y)``."""
@@ -163,7 +163,12 @@ def uvit_forward(sd: Dict[str, torch.Tensor], cfg: dict, x: torch.Tensor, timest
     x = _layer_norm(x, sd["norm.weight"], sd["norm.bias"])
 
     y = None
-    if mask_token is not None:
+    if mask_token is not None and use_ground_truth:
+        # libs/uvit_t2i.py:486-496: decode image feature + mask feature, hand the given mask back as the "prediction"
+        mask_feature = x[:, extras + L:] if not separate else m
+        noise = _linear(x[:, extras:extras + L] + mask_feature, sd["decoder_pred.weight"], sd["decoder_pred.bias"])
+        y = mask_token
+    elif mask_token is not None:
         if not separate:
             noise = _linear(x[:, extras:extras + L], sd["decoder_pred.weight"], sd["decoder_pred.bias"])
             y = _linear(x[:, extras + L:], sd["decoder_pred_mask.weight"], sd["decoder_pred_mask.bias"])

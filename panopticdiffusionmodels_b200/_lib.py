@@ -14,6 +14,7 @@ LIB_PATH = os.environ.get("PDM_LIB") or os.path.join(HERE, "libpdm.so")  # PDM_L
 
 PREC_BF16 = 0
 PREC_FP32 = 1
+FWD_GROUND_TRUTH = 1  # PDM_FWD_GROUND_TRUTH
 PLAN_STRIDE = 16
 ABI_VERSION = 1
 
@@ -33,6 +34,7 @@ SIGNATURES = {
     "pdm_finalize_params": (C.c_int, [_P, _P]),
     "pdm_workspace_bytes": (C.c_int, [_P, C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]),
     "pdm_nnet_forward": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P]),
+    "pdm_nnet_forward_ex": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P]),
     "pdm_cfg_update": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(C.c_float), C.c_float,
                                  C.c_int64, C.c_int64, _P]),
     "pdm_multistep_update": (C.c_int, [_P] * 14 + [C.POINTER(C.c_float), C.c_float, C.c_int64, C.c_int64, _P]),

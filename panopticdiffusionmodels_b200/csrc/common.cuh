@@ -138,6 +138,7 @@ struct HeadArgs {
     const float* m;       // [nb, Lm, D] mask tokens at offset m_off (null: image only)
     int Lm, m_off;
     bool ln_m;            // apply the final LayerNorm to the mask tokens too (single-stream)
+    bool gt;              // use_ground_truth (libs/uvit_t2i.py:486-496): decode image + mask features, no mask decoder
     const float* ln_w;
     const float* ln_b;
     const float* w_dec;   // [p*p*C, D]

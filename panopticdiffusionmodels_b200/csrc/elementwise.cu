@@ -409,7 +409,7 @@ __global__ void __launch_bounds__(256) head_token_kernel(HeadArgs a) {
     const int gpr = (P + HEAD_T - 1) / HEAD_T;  // token groups per (stream, sample)
     const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
-    const int nstream = a.m ? 2 : 1;
+    const int nstream = (a.m && !a.gt) ? 2 : 1;
     if (warp >= a.nb * gpr * nstream) return;
     const int stream = warp / (a.nb * gpr);
     const int rem = warp - stream * a.nb * gpr;
@@ -455,6 +455,55 @@ __global__ void __launch_bounds__(256) head_token_kernel(HeadArgs a) {
                     v[t][i].y = (v[t][i].y - mean) * rstd * w4.y + b4.y;
                     v[t][i].z = (v[t][i].z - mean) * rstd * w4.z + b4.z;
                     v[t][i].w = (v[t][i].w - mean) * rstd * w4.w + b4.w;
+                }
+            }
+        }
+    }
+    if (a.gt && a.m) {
+        // ground-truth mode: image feature + mask feature (mask tokens normalised only in the single-stream topology)
+#pragma unroll
+        for (int t = 0; t < HEAD_T; ++t) {
+            const int pidx = min(p0 + t, P - 1);
+            const float* row = a.m + ((long long)b * a.Lm + a.m_off + pidx) * D;
+            float4 u[NV];
+            float sum = 0.f;
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                const int c = lane + 32 * i;
+                u[i] = c * 4 < D ? __ldg(reinterpret_cast<const float4*>(row) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                sum += (u[i].x + u[i].y) + (u[i].z + u[i].w);
+            }
+            float mean = 0.f, rstd = 1.f;
+            if (a.ln_m) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                mean = sum / (float)D;
+                float sq = 0.f;
+#pragma unroll
+                for (int i = 0; i < NV; ++i) {
+                    const int c = lane + 32 * i;
+                    if (c * 4 < D) {
+                        const float e0 = u[i].x - mean, e1 = u[i].y - mean, e2 = u[i].z - mean, e3 = u[i].w - mean;
+                        sq += (e0 * e0 + e1 * e1) + (e2 * e2 + e3 * e3);
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+                rstd = rsqrtf(sq / (float)D + 1e-5f);
+            }
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                const int c = lane + 32 * i;
+                if (c * 4 < D) {
+                    if (a.ln_m) {
+                        const float4 w4 = __ldg(reinterpret_cast<const float4*>(a.ln_w) + c);
+                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.ln_b) + c);
+                        u[i].x = (u[i].x - mean) * rstd * w4.x + b4.x;
+                        u[i].y = (u[i].y - mean) * rstd * w4.y + b4.y;
+                        u[i].z = (u[i].z - mean) * rstd * w4.z + b4.z;
+                        u[i].w = (u[i].w - mean) * rstd * w4.w + b4.w;
+                    }
+                    v[t][i].x += u[i].x; v[t][i].y += u[i].y; v[t][i].z += u[i].z; v[t][i].w += u[i].w;
                 }
             }
         }
@@ -548,7 +597,7 @@ __global__ void __launch_bounds__(256) conv3x3_kernel(const float* __restrict__ 
 void head_decode(const HeadArgs& a, cudaStream_t s) {
     const int g = a.S / a.p;
     const int P = g * g;
-    const int nwarps = a.nb * ceil_div(P, HEAD_T) * (a.m ? 2 : 1);
+    const int nwarps = a.nb * ceil_div(P, HEAD_T) * ((a.m && !a.gt) ? 2 : 1);
     PDM_REQUIRE(a.D % 4 == 0 && a.D <= 1024, "head: D must be a multiple of 4 and <= 1024");
     const int nv = ceil_div(a.D, 128);
     const int hgrid = ceil_div(nwarps, 8);
@@ -564,7 +613,7 @@ void head_decode(const HeadArgs& a, cudaStream_t s) {
                                                                         a.C, a.S, 0);
         check_launch("conv3x3_img");
     }
-    if (a.m) {
+    if (a.m && !a.gt) {
         const long long total = (long long)a.nb * a.Cm * a.S * a.S;
         conv3x3_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, s>>>(a.tmp_msk, a.w_finm, a.b_finm, a.out_msk,
                                                                         a.nb, a.Cm, a.S, 1);

@@ -677,7 +677,7 @@ struct pdm_engine {
 
     // ws.ctxtok must be ready.  img/mask: [Bx, ...] inputs, evaluated for nb rows (row b uses input b % Bx).
     void forward(Workspace& ws, const float* img, const float* mask, int Bx, int nb, const float* t_dev, float t_scalar,
-                 float* out_noise, float* out_mask, int prec, cudaStream_t s) {
+                 float* out_noise, float* out_mask, int prec, cudaStream_t s, bool gt = false) {
         const bool with_mask = mask != nullptr;
         const bool two_m = two && with_mask;
         const bool b16 = prec == PDM_PREC_BF16;
@@ -747,7 +747,7 @@ struct pdm_engine {
             HeadArgs a;
             a.x = ws.x; a.Lx = Lx; a.x_off = ext;
             a.m = with_mask ? (two_m ? ws.mx : ws.x) : nullptr;
-            a.Lm = two_m ? L2 : Lx; a.m_off = ext + P; a.ln_m = !two_m;
+            a.Lm = two_m ? L2 : Lx; a.m_off = ext + P; a.ln_m = !two_m; a.gt = gt && with_mask;
             a.ln_w = params.at("norm.weight").d32; a.ln_b = params.at("norm.bias").d32;
             a.w_dec = params.at("decoder_pred.weight").d32; a.b_dec = params.at("decoder_pred.bias").d32;
             a.w_fin = params.at("final_layer.weight").d32; a.b_fin = params.at("final_layer.bias").d32;
@@ -977,6 +977,26 @@ int pdm_nnet_forward(pdm_handle h, const float* x, const float* t, const float* 
         PDM_CHECK_CUDA(cudaMemcpyAsync(ws.ctx_all, ctx, (size_t)n * h->T * h->cfg.clip_dim * 4, cudaMemcpyDeviceToDevice, s));
         h->compute_ctxtok(ws, n, precision, s);
         h->forward(ws, x, mask, n, n, t, 0.f, out_noise, out_mask, precision, s);
+    });
+}
+
+int pdm_nnet_forward_ex(pdm_handle h, const float* x, const float* t, const float* ctx, const float* mask, float* out_noise,
+                        float* out_mask, int32_t n, int32_t precision, int32_t flags, void* stream) {
+    return guard([&] {
+        PDM_REQUIRE(h && x && t && ctx && out_noise && n > 0, "null argument");
+        PDM_REQUIRE(h->finalized, "parameters not finalized");
+        PDM_REQUIRE(precision == PDM_PREC_BF16 || precision == PDM_PREC_FP32, "bad precision");
+        PDM_REQUIRE(!mask || h->cfg.enable_panoptic, "model built with enable_panoptic=False cannot take a mask");
+        PDM_REQUIRE(!mask || out_mask, "out_mask required when mask is given");
+        PDM_REQUIRE((flags & ~PDM_FWD_GROUND_TRUTH) == 0, "unknown forward flag");
+        const bool gt = (flags & PDM_FWD_GROUND_TRUTH) != 0 && mask != nullptr;
+        cudaStream_t s = (cudaStream_t)stream;
+        Workspace& ws = h->workspace(n, precision, mask != nullptr);
+        PDM_CHECK_CUDA(cudaMemcpyAsync(ws.ctx_all, ctx, (size_t)n * h->T * h->cfg.clip_dim * 4, cudaMemcpyDeviceToDevice, s));
+        h->compute_ctxtok(ws, n, precision, s);
+        h->forward(ws, x, mask, n, n, t, 0.f, out_noise, out_mask, precision, s, gt);
+        if (gt)  // the "prediction" of the ground-truth mode is the mask it was given (libs/uvit_t2i.py:496)
+            PDM_CHECK_CUDA(cudaMemcpyAsync(out_mask, mask, (size_t)n * h->Cm * h->S * h->S * 4, cudaMemcpyDeviceToDevice, s));
     });
 }
 

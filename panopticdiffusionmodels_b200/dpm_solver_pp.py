@@ -265,8 +265,8 @@ class DPM_Solver:
         """Returns ``(x_0, pred_mask)`` like the reference (dpm_solver_pp.py:1044)."""
         if solver_type != "dpm_solver":
             raise NotImplementedError("solver_type 'taylor' is not on the sampling hot path")
-        if use_ground_truth or use_twophases:
-            raise NotImplementedError("ground-truth / two-phase mask modes are outside the sampling hot path")
+        if use_twophases and method != "singlestep":
+            use_twophases = False  # the reference only looks at the flag in the singlestep driver (dpm_solver_pp.py:1071)
         if denoise:
             raise NotImplementedError("denoise=True is unreachable in the reference for these methods")
         if method == "multistep":
@@ -279,15 +279,21 @@ class DPM_Solver:
             raise RuntimeError("DPM_Solver (libpdm) has no CPU path: x must be a CUDA tensor")
         plan = build_plan(self.noise_schedule, steps, order, eps, T, skip_type, method,
                           mask_opt=bool(enable_mask_opt) or mask_token is None, n_time=self.n_time)
-        if mask_token is not None and not enable_mask_opt:
-            return self._sample_callback(x, mask_token, plan, enable_panoptic)  # pass-through encodings need slot 11
-        if getattr(self.model, "_pdm_fast_path", False):
+        fast = (getattr(self.model, "_pdm_fast_path", False) and not use_ground_truth and not use_twophases
+                and not (mask_token is not None and not enable_mask_opt))  # pass-through encodings need slot 11
+        if fast:
             return self.model.run_plan(x, mask_token, plan, use_graph=self.use_graph)
-        return self._sample_callback(x, mask_token, plan, enable_panoptic)
+        x, pred_mask, mask_t = self._sample_callback(x, mask_token, plan, enable_panoptic, use_ground_truth)
+        if use_twophases and mask_token is not None:
+            # phase two (dpm_solver_pp.py:1071-1075): the same time grid again, starting from the phase-one image, with the
+            # phase-one mask held fixed and fed to the network as ground truth; the returned pred_mask is phase one's
+            plan2 = build_plan(self.noise_schedule, steps, order, eps, T, skip_type, method, mask_opt=False, n_time=self.n_time)
+            x, _, _ = self._sample_callback(x, mask_t, plan2, True, True)
+        return x, pred_mask
 
     # ---- generic model_fn: Python loop, fused K12 kernel per evaluation ----------------------------
     @torch.no_grad()
-    def _sample_callback(self, x, mask_token, plan, enable_panoptic):
+    def _sample_callback(self, x, mask_token, plan, enable_panoptic, use_ground_truth=False):
         L = _lib.lib()
         dev = x.device
         f32 = dict(device=dev, dtype=torch.float32)
@@ -308,8 +314,8 @@ class DPM_Solver:
                 cur_x = xbase if stage == 0 else xin
                 cur_m = (mbase if stage == 0 else min_) if has_mask else None
                 t_cont = torch.full((B,), float(rec[0]) / self.n_time, **f32)
-                noise, pm = self.model(cur_x, t_cont, panoptic=pred_mask, mask_token=cur_m, use_ground_truth=False,
-                                       enable_panoptic=enable_panoptic)
+                noise, pm = self.model(cur_x, t_cont, panoptic=pred_mask, mask_token=cur_m,
+                                       use_ground_truth=use_ground_truth, enable_panoptic=enable_panoptic)
                 noise = noise.to(**f32).contiguous()
                 pm = pm.to(**f32).contiguous() if (has_mask and pm is not None) else None
                 coef = np.array(rec, dtype=np.float32)
@@ -332,7 +338,7 @@ class DPM_Solver:
                         mbase.numel() if has_mask else 0, _lib.current_stream()))
                 if stage == 0 and has_mask:
                     pred_mask = P0
-        return xbase, (P0 if has_mask else None)
+        return xbase, (P0 if has_mask else None), (mbase if has_mask else None)
 
     # ---- multistep 2M / 3M (dpm_solver_pp.py:602-677, driver :995-1017 repaired) ----------
     @torch.no_grad()

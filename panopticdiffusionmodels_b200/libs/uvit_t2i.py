@@ -211,8 +211,8 @@ class UViT(nn.Module):
     @torch.no_grad()
     def forward(self, x, timesteps, context, mask_token=None, mask_0=None, use_ground_truth=False,
                 enable_panoptic=False):
-        if use_ground_truth:
-            raise NotImplementedError("use_ground_truth=True (uvit_t2i.py:486-496) is outside the sampling hot path")
+        # the reference stores the per-call flag on the module (libs/uvit_t2i.py:380); it only matters with a mask_token
+        self.use_ground_truth = bool(use_ground_truth)
         if mask_token is not None and not self.enable_panoptic:
             raise TypeError("this UViT was built with enable_panoptic=False and cannot take mask_token")
         if x.dim() == 3:
@@ -240,7 +240,8 @@ class UViT(nn.Module):
                 raise ValueError("mask_token must be (B, num_panoptic_class, img_size, img_size) (SURVEY F4)")
             y = torch.empty_like(mask_token)
         with torch.cuda.device(dev):
-            _lib.check(_lib.lib().pdm_nnet_forward(
+            flags = _lib.FWD_GROUND_TRUTH if (use_ground_truth and mask_token is not None) else 0
+            _lib.check(_lib.lib().pdm_nnet_forward_ex(
                 h, _lib.ptr(x), _lib.ptr(t), _lib.ptr(context), _lib.ptr(mask_token), _lib.ptr(noise), _lib.ptr(y),
-                B, self.prec_code(), _lib.current_stream()))
+                B, self.prec_code(), flags, _lib.current_stream()))
         return noise if y is None else (noise, y)

@@ -41,8 +41,9 @@ class CFGModel:
     def __call__(self, x, t_continuous, panoptic=None, mask_token=None, use_ground_truth=False, enable_panoptic=False):
         t = t_continuous * self.n_time
         B = x.shape[0]
+        gt = bool(use_ground_truth)
         if self.empty_context is None:
-            out = self.nnet(x, t, self.context, mask_token=mask_token)
+            out = self.nnet(x, t, self.context, mask_token=mask_token, use_ground_truth=gt)
             return out if mask_token is not None else (out, None)
         # cond + uncond as one 2B batch (bit-identical to two B forwards: no cross-sample op)
         ctx2 = torch.cat([self.context, self.empty_context.unsqueeze(0).expand(B, -1, -1)], dim=0)
@@ -52,7 +53,7 @@ class CFGModel:
             out = self.nnet(x2, t2, ctx2)
             c, u = out[:B], out[B:]
             return c + self.scale * (c - u), None
-        noise, y = self.nnet(x2, t2, ctx2, mask_token=torch.cat([mask_token, mask_token], dim=0))
+        noise, y = self.nnet(x2, t2, ctx2, mask_token=torch.cat([mask_token, mask_token], dim=0), use_ground_truth=gt)
         c, u, pc, pu = noise[:B], noise[B:], y[:B], y[B:]
         return c + self.scale * (c - u), pc + self.scale * (pc - pu)
 

@@ -101,6 +101,29 @@ def main():
             res[f"z{steps}"] = z.numpy()
             res[f"pm{steps}"] = pm.numpy()
 
+        # --- ground-truth evaluation (libs/uvit_t2i.py:486-496) and the two-phase singlestep driver (dpm_solver_pp.py:1045-1078)
+        with torch.no_grad():
+            noise_gt, y_gt = net(x, t, ctx, mask_token=m, use_ground_truth=True)
+        assert torch.equal(y_gt, m)
+        res["noise_gt"] = noise_gt.numpy()
+
+        def model_fn_gt(xx, t_cont, panoptic=None, mask_token=None, use_ground_truth=False, enable_panoptic=False):
+            tt = t_cont * 1000
+            ec = empty.unsqueeze(0).expand(xx.shape[0], -1, -1)
+            c, pc = net(xx, tt, context=ctx, mask_token=mask_token, use_ground_truth=use_ground_truth)
+            u, pu = net(xx, tt, context=ec, mask_token=mask_token, use_ground_truth=use_ground_truth)
+            return c + scale * (c - u), pc + scale * (pc - pu)
+
+        for order, steps in ((3, 9), (2, 8), (1, 4)):
+            solver = dpm.DPM_Solver(model_fn_gt, ns, predict_x0=True, thresholding=False)
+            with torch.no_grad():
+                z, pm = solver.sample(x.clone(), steps=steps, eps=1e-3, T=1.0, order=order, method="singlestep",
+                                      mask_token=m.clone(), enable_mask_opt=True, enable_panoptic=True, use_twophases=True)
+                z1, pm1 = solver.sample(x.clone(), steps=steps, eps=1e-3, T=1.0, order=order, method="singlestep",
+                                        mask_token=m.clone(), enable_mask_opt=True, enable_panoptic=True)
+            res[f"z_tp{order}"], res[f"pm_tp{order}"] = z.numpy(), pm.numpy()
+            res[f"z_ss{order}"], res[f"pm_ss{order}"] = z1.numpy(), pm1.numpy()
+
         sd = {k: v.detach().numpy() for k, v in net.state_dict().items()}
         np.savez_compressed(
             os.path.join(HERE, f"tiny_{name}.npz"),

@@ -47,6 +47,30 @@ def test_joint_sample_matches_reference(name, separate, steps):
     assert (pm - ref_pm).abs().max() <= 2e-4
 
 
+@pytest.mark.parametrize("name,separate", [("single", False), ("two", True)])
+def test_ground_truth_forward_matches_reference(name, separate):
+    """use_ground_truth=True evaluation (libs/uvit_t2i.py:486-496): fixture = the real reference's output."""
+    g, sd = load_golden(f"tiny_{name}.npz")
+    cfg = dict(TINY, separate=separate)
+    noise, y = uvit_oracle.uvit_forward(sd, cfg, g["x"], g["t"], g["ctx"], g["m"], use_ground_truth=True)
+    assert torch.allclose(noise, g["noise_gt"], rtol=0, atol=2e-6)
+    assert torch.equal(y, g["m"])
+
+
+@pytest.mark.parametrize("name,separate", [("single", False), ("two", True)])
+@pytest.mark.parametrize("order,steps", [(3, 9), (2, 8), (1, 4)])
+def test_singlestep_and_two_phase_match_reference(name, separate, order, steps):
+    """method='singlestep' with and without use_twophases (dpm_solver_pp.py:1045-1078), fixtures from the reference."""
+    g, sd = load_golden(f"tiny_{name}.npz")
+    cfg = dict(TINY, separate=separate)
+    model = dpm_oracle.cfg_model(sd, cfg, g["ctx"], g["empty"], float(g["scale"]))
+    for two, tag in ((False, "ss"), (True, "tp")):
+        z, pm = dpm_oracle.Solver(model, dpm_oracle.Schedule()).sample_singlestep(g["x"], g["m"], steps, order, two_phases=two)
+        ref_z, ref_pm = g[f"z_{tag}{order}"], g[f"pm_{tag}{order}"]
+        assert (z - ref_z).abs().max() <= 2e-4 * ref_z.abs().max(), (tag, order)
+        assert (pm - ref_pm).abs().max() <= 2e-4, (tag, order)
+
+
 def test_multistep_bit_exact():
     g, _ = load_golden("multistep.npz")
     s = dpm_oracle.Solver(None, dpm_oracle.Schedule())
