@@ -184,10 +184,12 @@ def run_ours(a):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # keep stdout to the ONE JSON line: NCCL writes its version banner to the C-level stdout whenever NCCL_DEBUG >= VERSION
+    # (WARN included), so file descriptor 1 is pointed at stderr for the whole run and the JSON line goes to the saved one
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        # keep stdout to the ONE JSON line: NCCL prints its version banner there at NCCL_DEBUG=VERSION
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     cfg, kw = nnet_kwargs(a)
     B = a.batch or default_batch(a.config, a.gpus)
@@ -313,10 +315,12 @@ def run_ours(a):
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "kernels": kern,
             "cpu_baseline": None if cb is None else {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
         }
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    os.close(json_fd)
 
 
 def main():
