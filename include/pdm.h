@@ -74,7 +74,9 @@ int pdm_destroy(pdm_handle h);
  * (mask_embed_0.*, even-indexed zero_convs.*) are accepted and ignored. */
 int pdm_set_param(pdm_handle h, const char* key, const void* dev_f32, const int64_t* shape, int32_t ndim,
                   void* stream);
-/* checks that every parameter the graph needs was set; builds bf16 operands.  Synchronises `stream`. */
+/* checks that every parameter the graph needs was set; builds the derived operands (bf16 copies, the LayerNorm-folded
+ * qkv / fc1 weights of the deferred-LayerNorm path, transposed patch-embed weights).  Must be called again after any
+ * pdm_set_param: evaluations are refused in between.  Synchronises `stream`. */
 int pdm_finalize_params(pdm_handle h, void* stream);
 
 /* bytes of private workspace the engine will hold for `n` network rows (n = samples in one forward) */

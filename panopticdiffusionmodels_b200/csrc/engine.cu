@@ -253,6 +253,9 @@ struct pdm_engine {
             convert_f32_bf16(p.d32, p.d16, (long long)p.n, s);
         }
         p.set = true;
+        // derived tensors (LayerNorm-folded qkv / fc1 weights, transposed patch-embed weights) are rebuilt by
+        // pdm_finalize_params: evaluations are refused until it has been called again
+        finalized = false;
         // cached graphs bake nothing about weights (pointers are stable), so they stay valid.
     }
     LinearW lin(const std::string& w, const std::string& b, int N, int K) {
