@@ -27,6 +27,8 @@ namespace pdm {
 
 CUtensorMap make_tmap_bf16_3d(const void* ptr, long long K, long long rows, long long nbatch, long long bs,
                               int box_rows, int box_k);
+CUtensorMap make_tmap_3d(const void* ptr, int esize, long long K, long long rows, long long nbatch, long long bs,
+                         int box_rows, int box_k, CUtensorMapSwizzle swz);
 
 namespace {
 
@@ -37,7 +39,8 @@ constexpr int BN = 256, BK = 64;
 #endif
 constexpr int A_BYTES = BM * BK * 2;
 constexpr int SCR_STRIDE = 36;  // 32-bit words per scratch row: 128 B payload + 16 B pad (16 B aligned, conflict-free)
-enum { EPI_F32 = 0, EPI_PACK = 1, EPI_LN = 2, EPI_LN_GELU = 3, EPI_F32_EMIT = 4, EPI_LN_GELU_W16 = 5 };
+enum { EPI_F32 = 0, EPI_PACK = 1, EPI_LN = 2, EPI_LN_GELU = 3, EPI_F32_EMIT = 4, EPI_LN_GELU_W16 = 5, EPI_F32_TMA = 6 };
+constexpr int TMA_WARP_BYTES = 3 * 4096 + 2048;  // EPI_F32_TMA: 3 fp32 [32 x 32] staging tiles + 1 bf16 [32 x 32] tile per warp
 
 // Epilogue geometry per form.  Each epilogue warp covers one TMEM lane quarter x WCOLS accumulator columns.  The
 // fc1 form (LN + GELU, bf16 out) is latency-bound per warp (TMEM load -> FMA / tanh chain -> pack -> transpose, 94 registers):
@@ -52,7 +55,9 @@ struct Geo {
     static constexpr int WCOLS = 256 / (EW / 4);  // accumulator columns per epilogue warp
     static constexpr int NBLK = WCOLS / 32;       // 32-column blocks per epilogue warp
     static constexpr int THREADS = 64 + EW * 32;
-    static constexpr int SCR_WORDS = 32 * SCR_STRIDE + WCOLS;  // transpose scratch + this warp's slice of the bias vector
+    static constexpr bool TMA = EPI == EPI_F32_TMA;
+    // transpose scratch (or the TMA staging tiles) + this warp's slice of the bias vector
+    static constexpr int SCR_WORDS = TMA ? (TMA_WARP_BYTES + 1024) / 4 : 32 * SCR_STRIDE + WCOLS;  // TMA: 1024-aligned per warp
     static constexpr int SCR_BYTES = SCR_WORDS * 4;
     static_assert(EW == 8 || EW == 16, "epilogue warps: 8 or 16");
     static_assert(LN || WCOLS == LN_PART, "the LayerNorm partial sums are per (fp32-form) epilogue-warp column slice");
@@ -63,8 +68,8 @@ template <int NCTA, int EPI>
 struct Cfg {
     static constexpr int B_BYTES = (BN / NCTA) * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = NCTA == 2 ? (Geo<EPI>::EW > 8 ? 4 : 5) : 3;
-    static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + Geo<EPI>::EW * Geo<EPI>::SCR_BYTES + 256;
+    static constexpr int STAGES = NCTA == 2 ? (Geo<EPI>::TMA ? 3 : (Geo<EPI>::EW > 8 ? 4 : 5)) : (Geo<EPI>::TMA ? 2 : 3);
+    static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + Geo<EPI>::EW * Geo<EPI>::SCR_BYTES + 512;
     static_assert(SMEM_BYTES <= 232448, "dynamic shared memory budget");
 };
 
@@ -174,7 +179,9 @@ __device__ __forceinline__ void release_accumulator(uint64_t* tempty_bar, uint32
 template <int NCTA, int EPI>
 __global__ void __cluster_dims__(NCTA, 1, 1) __launch_bounds__(Geo<EPI>::THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
-               const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO32,
+               const __grid_constant__ CUtensorMap tmO32b, const __grid_constant__ CUtensorMap tmO2,
+               const __grid_constant__ CUtensorMap tmO2b, const TcParams p) {
     using C = Cfg<NCTA, EPI>;
     using G = Geo<EPI>;
     constexpr int EPI_WARPS = G::EW, WCOLS = G::WCOLS, NBLK = G::NBLK, SCR_BYTES = G::SCR_BYTES;
@@ -193,6 +200,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     uint64_t* tfull = bars + 2 * STAGES;       // [2]       each CTA its own; MMA commit (multicast)
     uint64_t* tempty = bars + 2 * STAGES + 2;  // [2]       leader's; all epilogue warps of the pair arrive
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    uint64_t* resbar = bars + 2 * STAGES + 5;  // [EPI_WARPS][3]  EPI_F32_TMA: residual tile landed (TMA complete_tx)
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -213,6 +221,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&tfull[i], 1);
             ptx::mbar_init(&tempty[i], NCTA * EPI_WARPS);
+        }
+        if (G::TMA) {
+            for (int i = 0; i < EPI_WARPS * 3; ++i) ptx::mbar_init(&resbar[i], 1);
+            ptx::prefetch_tmap(&tmO32);
+            ptx::prefetch_tmap(&tmO2);
         }
         ptx::fence_mbar_init();
     }
@@ -319,8 +332,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         const int q = warp & 3;    // TMEM lane quarter this warp may access
         const int half = ew >> 2;  // which WCOLS-column slice of the tile
         uint32_t* scr = reinterpret_cast<uint32_t*>(scr_base + ew * SCR_BYTES);
-        float* sbias = reinterpret_cast<float*>(scr + 32 * SCR_STRIDE);  // [WCOLS]
-        constexpr bool packed = EPI != EPI_F32 && EPI != EPI_F32_EMIT;
+        float* sbias = reinterpret_cast<float*>(scr + (G::TMA ? TMA_WARP_BYTES / 4 : 32 * SCR_STRIDE));  // [WCOLS]
+        constexpr bool packed = EPI != EPI_F32 && EPI != EPI_F32_EMIT && EPI != EPI_F32_TMA;
         constexpr bool EMIT = EPI == EPI_F32_EMIT;
         constexpr bool LN = G::LN;
         // deferred LayerNorm: 1 / std of the accumulator row this thread owns, fetched ONE TILE AHEAD into a register (read
@@ -341,6 +354,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         float rstd_next = 0.f;
         if (LN) rstd_next = load_rstd(unit_id);
         const int rsub = lane >> 3, c8 = lane & 7;
+        uint32_t tma_g = 0;  // EPI_F32_TMA: chunks this warp has processed (staging-buffer / barrier-phase counter)
+        if (G::TMA && p.accumulate && lane == 0 && unit_id < p.total_tiles) {
+            const int mp = unit_id / p.ntn, nt = unit_id - mp * p.ntn;
+            const int mt = NCTA * mp + (int)rank;
+            const int c0 = nt * BN + half * WCOLS;
+            const int b0 = mt < p.n_mtiles ? mt / p.tpb : 0;
+            const int r0 = (mt < p.n_mtiles ? (mt - b0 * p.tpb) * BM : p.tpb * BM) + q * 32;
+            if (c0 < p.N) {
+                uint64_t* rb0 = resbar + ew * 3;
+                ptx::mbar_expect_tx(rb0, 4096);
+                ptx::tma_load_3d(&tmO32, rb0, ptx::smem_u32(scr), c0, r0, b0);
+            }
+        }
         int it = 0;
         for (int tile = unit_id; tile < p.total_tiles; tile += n_units, ++it) {
             const int mp = tile / p.ntn, nt = tile - mp * p.ntn;
@@ -354,7 +380,113 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
             const int trow0 = t0 + q * 32;
             const int ncol0 = nt * BN + half * WCOLS;  // first column of this warp's slice
             const uint32_t tbase = tmem_base + (uint32_t(q * 32) << 16) + as * BN + half * WCOLS;
-            if constexpr (packed) {
+            if constexpr (G::TMA) {
+                // ---- fp32 read-modify-write through TMA: the residual tile comes in by TMA (one chunk ahead, no registers),
+                // the thread that owns accumulator row `lane` adds it in the row domain (swizzled, conflict-free LDS / STS),
+                // the fp32 result and its bf16 copy go out by TMA stores.  No transpose, no global address arithmetic, no
+                // row / column predicates (the tensor maps clip), LayerNorm row sums without shuffles.
+                const uint32_t wbase = ptx::smem_u32(scr);             // 3 x [32 rows][128 B] fp32, SWIZZLE_128B (1024-aligned)
+                const uint32_t hbase = wbase + 3 * 4096;               // [32 rows][64 B] bf16, SWIZZLE_64B
+                uint64_t* rb = resbar + ew * 3;
+                const bool active = ncol0 < p.N;
+                const int row_t = (tile_ok ? t0 : p.tpb * BM) + q * 32;  // padding tile: out of bounds -> loads zero-fill, stores clip
+                const int sw = (lane & 7) << 4, swh = ((lane >> 1) & 3) << 4;
+                if (active) {
+#pragma unroll
+                    for (int i = 0; i < NBLK; ++i) {
+                        const int c = ncol0 + lane + 32 * i;
+                        sbias[lane + 32 * i] = (p.bias && c < p.N) ? __ldg(p.bias + c) : 0.f;
+                    }
+                }
+                float s1 = 0.f, s2 = 0.f;
+                // chunk 0 of this warp's slice of tile `ntile` -> staging buffer / barrier `idx` (lane 0 only)
+                auto prefetch_tile = [&](int ntile, uint32_t idx) {
+                    if (ntile >= p.total_tiles) return;
+                    const int mp2 = ntile / p.ntn, nt2 = ntile - mp2 * p.ntn;
+                    const int mt2 = NCTA * mp2 + (int)rank;
+                    const int ncol = nt2 * BN + half * WCOLS;
+                    if (ncol >= p.N) return;
+                    const int nb_ = mt2 < p.n_mtiles ? mt2 / p.tpb : 0;
+                    const int nrow = (mt2 < p.n_mtiles ? (mt2 - nb_ * p.tpb) * BM : p.tpb * BM) + q * 32;
+                    ptx::mbar_expect_tx(&rb[idx], 4096);
+                    ptx::tma_load_3d(&tmO32, &rb[idx], wbase + idx * 4096u, ncol, nrow, nb_);
+                };
+                const int nch = active ? min(NBLK, (p.N - ncol0 + 31) / 32) : 0;
+                ptx::mbar_wait(&tfull[as], aphase);
+                ptx::tc_fence_after();
+                if (nch == 0) {
+                    release_accumulator<NCTA>(&tempty[as], rank, lane);
+                    // nothing to do in this tile: keep the residual pipeline primed for the next one
+                    if (p.accumulate && lane == 0) prefetch_tile(tile + n_units, tma_g % 3u);
+                }
+#pragma unroll 1
+                for (int chunk = 0; chunk < nch; ++chunk) {
+                    const int col = ncol0 + 32 * chunk;
+                    const uint32_t rcur = wbase + (tma_g % 3u) * 4096u;
+                    // (1) request the residual tile of the NEXT chunk (same tile, or chunk 0 of this warp's next tile)
+                    if (p.accumulate && lane == 0) {
+                        const uint32_t idx = (tma_g + 1u) % 3u;
+                        if (chunk + 1 < nch) {
+                            ptx::mbar_expect_tx(&rb[idx], 4096);
+                            ptx::tma_load_3d(&tmO32, &rb[idx], wbase + idx * 4096u, col + 32, row_t, b);
+                        } else {
+                            prefetch_tile(tile + n_units, idx);
+                        }
+                    }
+                    // (2) accumulator chunk -> registers; (3) the residual of this chunk has landed
+                    uint32_t v[32];
+                    ptx::tmem_ld_32x32(tbase + chunk * 32, v);
+                    if (p.accumulate) ptx::mbar_wait(&rb[tma_g % 3u], (tma_g / 3u) & 1u);
+                    ptx::tmem_ld_wait();
+                    if (chunk == nch - 1) release_accumulator<NCTA>(&tempty[as], rank, lane);
+                    // the bf16 staging tile is single-buffered: the previous chunk's stores must have read it (this also
+                    // retires the fp32 store of two chunks ago, whose buffer the next residual load will overwrite)
+                    if (lane == 0) ptx::bulk_wait_read0();
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const uint32_t addr = rcur + lane * 128 + ((j << 4) ^ sw);
+                        float4 a = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                               __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                        const float4 bb = *reinterpret_cast<const float4*>(sbias + 32 * chunk + 4 * j);
+                        add2(a.x, a.y, bb.x, bb.y);
+                        add2(a.z, a.w, bb.z, bb.w);
+                        if (p.accumulate) {
+                            float4 r;
+                            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                         : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr));
+                            add2(a.x, a.y, r.x, r.y);
+                            add2(a.z, a.w, r.z, r.w);
+                        }
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w) : "memory");
+                        s1 += (a.x + a.y) + (a.z + a.w);
+                        s2 = fmaf(a.x, a.x, fmaf(a.y, a.y, fmaf(a.z, a.z, fmaf(a.w, a.w, s2))));
+                        v[2 * j] = pack2(a.x, a.y);      // v[0 .. 2j+1] are dead: reuse them for the bf16 row
+                        v[2 * j + 1] = pack2(a.z, a.w);
+                        if (j & 1) {
+                            const uint32_t haddr = hbase + lane * 64 + (((j >> 1) << 4) ^ swh);
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(haddr), "r"(v[2 * j - 2]),
+                                         "r"(v[2 * j - 1]), "r"(v[2 * j]), "r"(v[2 * j + 1]) : "memory");
+                        }
+                    }
+                    ptx::fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        ptx::tma_store_3d(&tmO32, rcur, col, row_t, b);
+                        if (p.out32b) ptx::tma_store_3d(&tmO32b, rcur, col, row_t, b);
+                        if (p.out2) ptx::tma_store_3d(&tmO2, hbase, col, row_t, b);
+                        if (p.out2b) ptx::tma_store_3d(&tmO2b, hbase, col, row_t, b);
+                        ptx::bulk_commit();
+                    }
+                    ++tma_g;
+                }
+                if (p.stats && active && trow0 + lane < lr_eff) {
+                    const int part = ncol0 / LN_PART;
+                    reinterpret_cast<float2*>(p.stats)[((long long)b * p.stats_bs + trow0 + lane) * p.npart + part] = make_float2(s1, s2);
+                    if (p.statsb)
+                        reinterpret_cast<float2*>(p.statsb)[((long long)b * p.statsb_bs + trow0 + lane) * p.npart + part] = make_float2(s1, s2);
+                }
+            } else if constexpr (packed) {
                 // ---- bf16-only output: 2 chunks of 64 columns; bias/GELU in the row domain, pack, transpose ----
                 const bool has_bias = LN || p.bias != nullptr;
                 const bool gelu = LN ? G::GELU : (p.gelu != 0);
@@ -556,6 +688,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         }
     }
 
+    if (G::TMA && warp >= 2 && lane == 0) ptx::bulk_wait0();  // outstanding TMA stores read this CTA's shared memory
     ptx::tc_fence_before();
     if (NCTA == 2) ptx::cluster_sync(); else __syncthreads();
     if (warp == 1) {
@@ -635,6 +768,13 @@ void launch(const GemmProblem& g, cudaStream_t s) {
     const CUtensorMap tmA2 =
         g.A2 ? make_tmap_bf16_3d(g.A2, g.K2, g.Lr, g.nb, g.a2_bs ? g.a2_bs : g.Lr, BM, BK) : tmA1;
     const CUtensorMap tmB = make_tmap_bf16_3d(g.W16, K, g.N, 1, g.N, BN / NCTA, BK);
+    CUtensorMap tmO32 = tmA1, tmO32b = tmA1, tmO2 = tmA1, tmO2b = tmA1;
+    if (EPI == EPI_F32_TMA) {
+        tmO32 = make_tmap_3d(g.out32, 4, g.N, g.Lr, g.nb, p.out32_bs, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (g.out32b) tmO32b = make_tmap_3d(g.out32b, 4, g.N, g.Lr, g.nb, p.out32b_bs, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (g.out2) tmO2 = make_tmap_3d(g.out2, 2, g.N, g.Lr, g.nb, p.out2_bs, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+        if (g.out2b) tmO2b = make_tmap_3d(g.out2b, 2, g.N, g.Lr, g.nb, p.out2b_bs, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+    }
     static bool attr_set = false;
     if (!attr_set) {
         PDM_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<NCTA, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -642,13 +782,38 @@ void launch(const GemmProblem& g, cudaStream_t s) {
         attr_set = true;
     }
     const int units = std::max(1, std::min(p.total_tiles, num_sms() / NCTA));
-    gemm_tc_kernel<NCTA, EPI><<<NCTA * units, Geo<EPI>::THREADS, Cfg<NCTA, EPI>::SMEM_BYTES, s>>>(tmA1, tmA2, tmB, p);
+    gemm_tc_kernel<NCTA, EPI><<<NCTA * units, Geo<EPI>::THREADS, Cfg<NCTA, EPI>::SMEM_BYTES, s>>>(tmA1, tmA2, tmB, tmO32, tmO32b, tmO2, tmO2b, p);
     check_launch("gemm_tc");
 }
 
 }  // namespace
 
 // bf16 [nbatch][rows][K] view with batch stride bs rows; box = [box_k (K), box_rows, 1]; SWIZZLE_128B
+// element size 2 (bf16) or 4 (fp32); swizzle = CU_TENSOR_MAP_SWIZZLE_{128B, 64B}
+CUtensorMap make_tmap_3d(const void* ptr, int esize, long long K, long long rows, long long nbatch, long long bs,
+                         int box_rows, int box_k, CUtensorMapSwizzle swz) {
+    MapKey key(ptr, K * 16 + esize, rows, nbatch, bs, box_rows, box_k * 16 + (int)swz);
+    {
+        std::lock_guard<std::mutex> lk(g_map_mutex);
+        auto it = g_map_cache.find(key);
+        if (it != g_map_cache.end()) return it->second;
+    }
+    PDM_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "tensor map: base must be 16-byte aligned");
+    PDM_REQUIRE((K * esize) % 16 == 0, "tensor map: row pitch must be a multiple of 16 bytes");
+    CUtensorMap m;
+    cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)nbatch};
+    cuuint64_t strides[2] = {(cuuint64_t)(K * esize), (cuuint64_t)(bs * K * esize)};
+    cuuint32_t box[3] = {(cuuint32_t)box_k, (cuuint32_t)box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = get_encode()(&m, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                              const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    PDM_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (code " + std::to_string((int)r) + ")");
+    std::lock_guard<std::mutex> lk(g_map_mutex);
+    g_map_cache[key] = m;
+    return m;
+}
+
 CUtensorMap make_tmap_bf16_3d(const void* ptr, long long K, long long rows, long long nbatch, long long bs,
                               int box_rows, int box_k) {
     MapKey key(ptr, K, rows, nbatch, bs, box_rows, box_k);
@@ -678,6 +843,8 @@ void clear_tmap_cache() {
     g_map_cache.clear();
 }
 
+static int K_total(const GemmProblem& g) { return g.K1 + (g.A2 ? g.K2 : 0); }
+
 void gemm_tc_bf16(const GemmProblem& g, cudaStream_t s) {
     PDM_REQUIRE(g.A1 && g.W16 && g.Lr > 0 && g.nb > 0, "gemm_tc: bad problem");
     PDM_REQUIRE(g.N % 4 == 0, "gemm_tc: N must be a multiple of 4");
@@ -692,9 +859,18 @@ void gemm_tc_bf16(const GemmProblem& g, cudaStream_t s) {
     PDM_REQUIRE((!g.stats && !g.statsb && !g.out2b) || g.out32, "gemm_tc: row sums / out2b belong to the fp32-output form");
     PDM_REQUIRE(!g.statsb || g.stats, "gemm_tc: statsb needs stats");
     static const bool one_cta = getenv("PDM_GEMM_1CTA") != nullptr;
-    const int epi = g.out32 ? ((g.stats || g.out2b) ? EPI_F32_EMIT : EPI_F32) : (g.ln_rstd ? (g.gelu ? (g.K1 <= 512 ? EPI_LN_GELU_W16 : EPI_LN_GELU) : EPI_LN) : EPI_PACK);
+    // TMA-store epilogue: the HBM-bound read-modify-write GEMMs (proj, zero-conv: K <= 1024).  It leaves room for a 3-stage
+    // operand ring only, so the tensor-bound K >= 2048 forms (fc2) and the skip GEMM keep the register-transpose epilogue.
+    static const bool tma_epi = getenv("PDM_GEMM_NO_TMA_EPI") == nullptr;
+    static const int tma_maxk = getenv("PDM_GEMM_TMA_MAXK") ? atoi(getenv("PDM_GEMM_TMA_MAXK")) : 1024;
+    static const bool tma_noresid = getenv("PDM_GEMM_TMA_NORESID") != nullptr;
+    const bool tma_ok = tma_epi && g.out32 && (g.resid || tma_noresid) && !g.gelu && g.N % 32 == 0 && K_total(g) <= tma_maxk &&
+                        (!g.out2b || (g.out2b_row0 == 0 && g.out2b_mod == 0));
+    const int epi = g.out32 ? (tma_ok ? EPI_F32_TMA : ((g.stats || g.out2b) ? EPI_F32_EMIT : EPI_F32))
+                            : (g.ln_rstd ? (g.gelu ? (g.K1 <= 512 ? EPI_LN_GELU_W16 : EPI_LN_GELU) : EPI_LN) : EPI_PACK);
     if (one_cta) {
         if (epi == EPI_F32) launch<1, EPI_F32>(g, s);
+        else if (epi == EPI_F32_TMA) launch<1, EPI_F32_TMA>(g, s);
         else if (epi == EPI_F32_EMIT) launch<1, EPI_F32_EMIT>(g, s);
         else if (epi == EPI_PACK) launch<1, EPI_PACK>(g, s);
         else if (epi == EPI_LN) launch<1, EPI_LN>(g, s);
@@ -702,6 +878,7 @@ void gemm_tc_bf16(const GemmProblem& g, cudaStream_t s) {
         else launch<1, EPI_LN_GELU>(g, s);
     } else {
         if (epi == EPI_F32) launch<2, EPI_F32>(g, s);
+        else if (epi == EPI_F32_TMA) launch<2, EPI_F32_TMA>(g, s);
         else if (epi == EPI_F32_EMIT) launch<2, EPI_F32_EMIT>(g, s);
         else if (epi == EPI_PACK) launch<2, EPI_PACK>(g, s);
         else if (epi == EPI_LN) launch<2, EPI_LN>(g, s);
