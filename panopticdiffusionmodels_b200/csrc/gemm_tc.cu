@@ -9,10 +9,14 @@
 //               in pair mode completion bytes of both CTAs are credited to the leader's full barrier
 //   warp 1      TMEM allocator; (leader) one thread issues tcgen05.mma and commits: smem slot free / accumulator full
 //               (multicast to both CTAs in pair mode)
-//   warps 2..9  epilogue on the CTA's own 128 accumulator rows: tcgen05.ld -> per-warp smem transpose ->
-//               coalesced 128-bit global I/O.  All global loads the epilogue needs (bias, the fp32 residual tile)
-//               are issued BEFORE the accumulator is waited for / one chunk ahead, so their latency hides behind
-//               the MMAs.  bf16-only outputs are packed before the transpose (half the smem traffic).
+//   warps 2..   epilogue on the CTA's own 128 accumulator rows, one of several compile-time forms (EPI):
+//               F32 / F32_EMIT   fp32 output (optionally += in place; _EMIT: + bf16 copies + LayerNorm row sums):
+//                                tcgen05.ld -> per-warp smem transpose -> coalesced 128-bit global I/O; bias and the fp32
+//                                residual tile are fetched before the accumulator is waited for / one chunk ahead
+//               F32_TMA          the same contract for the HBM-bound K <= 1024 read-modify-write GEMMs (proj, zero-conv):
+//                                residual tile in by TMA, row-domain add on swizzled staging tiles, tiles out by TMA stores
+//               PACK / LN / LN_GELU[_W16]   bf16-only output, packed before the transpose; LN*: LayerNorm folded into the
+//                                weight, 1/std per accumulator row applied here; _W16: 16 epilogue warps (fc1, K <= 512)
 // Rings: STAGES-deep smem ring, 2-deep TMEM accumulator ring (2 x 256 columns).
 // The long-skip concat is never materialised (K loop streams A1 then A2); row views use the map's batch coordinate.
 #include <cstdlib>

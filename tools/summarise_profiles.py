@@ -66,6 +66,14 @@ def table(rep, title, cmd, fname, note):
 
 
 GEMM_LABELS = {  # launch order of `-k regex:gemm_tc -s 3000 -c 8` in the two-stream small config (deferred-LayerNorm flow)
+    "r01d": ["gemm_proj  mask stream  M=302080 N=K=512, fp32 RMW + bf16 copy + LN row sums, TMA-in / TMA-out epilogue   <2,F32_TMA>",
+             "gemm_fc1   mask stream  M=302080 N=2048 K=512, LN folded + GELU, bf16 out, 16 epilogue warps   <2,LN_GELU_W16>",
+             "gemm_fc2   mask stream  M=302080 N=512 K=2048, fp32 RMW + 2 bf16 copies + LN row sums   <2,EMIT>",
+             "gemm_zeroconv  M=512x334 rows, N=K=512, fp32 RMW + fp32/bf16 concat copies + LN row sums (x2), TMA epilogue   <2,F32_TMA>",
+             "gemm_qkv   image stream M=171008 N=1536 K=512, LN folded, bf16 out   <2,LN>",
+             "gemm_proj  image stream M=171008 N=K=512   <2,F32_TMA>",
+             "gemm_fc1   image stream M=171008 N=2048 K=512   <2,LN_GELU_W16>",
+             "gemm_fc2   image stream M=171008 N=512 K=2048, fp32 RMW only (zero-conv follows)   <2,F32>"],
     "r01c": ["gemm_proj  mask stream  M=302080 N=K=512, fp32 RMW + bf16 copy + LN row sums   <2,EMIT>",
              "gemm_fc1   mask stream  M=302080 N=2048 K=512, LN folded + GELU, bf16 out, 16 epilogue warps   <2,LN_GELU_W16>",
              "gemm_fc2   mask stream  M=302080 N=512 K=2048, fp32 RMW + 2 bf16 copies + LN row sums   <2,EMIT>",
