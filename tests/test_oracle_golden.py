@@ -1,6 +1,9 @@
 """Pins the oracle (oracle/*.py) to the reference: golden fixtures made by
 executing /root/reference (tests/golden/make_golden.py)."""
 import numpy as np
+import os
+import sys
+
 import pytest
 import torch
 
@@ -69,6 +72,23 @@ def test_singlestep_and_two_phase_match_reference(name, separate, order, steps):
         ref_z, ref_pm = g[f"z_{tag}{order}"], g[f"pm_{tag}{order}"]
         assert (z - ref_z).abs().max() <= 2e-4 * ref_z.abs().max(), (tag, order)
         assert (pm - ref_pm).abs().max() <= 2e-4, (tag, order)
+
+
+def test_config1_joint_sample_matches_reference():
+    """BASELINE config 1 (mscoco_uvit_small as shipped, random-init, batch 4, DPM-Solver++ 20 NFE, CFG 2.0, fp32 on CPU):
+    the oracle against the REAL reference's output (tests/golden/make_config1.py).  ~1 minute of CPU."""
+    import numpy as np
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_config1 import build_ours, inputs
+    net, kw = build_ours()
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    x, m, ctx, empty = inputs()
+    ref = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "config1_small_two.npz"))
+    torch.set_num_threads(os.cpu_count())
+    z, pm = dpm_oracle.joint_sample(sd, kw, x, m, ctx, empty, float(ref["scale"]), int(ref["steps"]))
+    ref_z, ref_pm = torch.from_numpy(ref["z"]), torch.from_numpy(ref["pm"])
+    assert (z - ref_z).abs().max() <= 5e-4 * ref_z.abs().max()
+    assert (pm - ref_pm).abs().max() <= 5e-4
 
 
 def test_multistep_bit_exact():
