@@ -60,8 +60,10 @@ struct Geo {
     static constexpr int NBLK = WCOLS / 32;       // 32-column blocks per epilogue warp
     static constexpr int THREADS = 64 + EW * 32;
     static constexpr bool TMA = EPI == EPI_F32_TMA;
+    static constexpr bool PTMA = EPI == EPI_LN_GELU_W16;  // bf16 tile leaves through a TMA store (no transpose readback)
     // transpose scratch (or the TMA staging tiles) + this warp's slice of the bias vector
-    static constexpr int SCR_WORDS = TMA ? (TMA_WARP_BYTES + 1024) / 4 : 32 * SCR_STRIDE + WCOLS;  // TMA: 1024-aligned per warp
+    // TMA forms: swizzled staging tiles, 1024-byte aligned per warp (PTMA: one [32 rows][128 B] bf16 tile + the bias slice)
+    static constexpr int SCR_WORDS = TMA ? (TMA_WARP_BYTES + 1024) / 4 : (PTMA ? (4096 + 1024) / 4 : 32 * SCR_STRIDE + WCOLS);
     static constexpr int SCR_BYTES = SCR_WORDS * 4;
     static_assert(EW == 8 || EW == 16, "epilogue warps: 8 or 16");
     static_assert(LN || WCOLS == LN_PART, "the LayerNorm partial sums are per (fp32-form) epilogue-warp column slice");
@@ -226,6 +228,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
             ptx::mbar_init(&tfull[i], 1);
             ptx::mbar_init(&tempty[i], NCTA * EPI_WARPS);
         }
+        if (G::PTMA) ptx::prefetch_tmap(&tmO2);
         if (G::TMA) {
             for (int i = 0; i < EPI_WARPS * 3; ++i) ptx::mbar_init(&resbar[i], 1);
             ptx::prefetch_tmap(&tmO32);
@@ -336,7 +339,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         const int q = warp & 3;    // TMEM lane quarter this warp may access
         const int half = ew >> 2;  // which WCOLS-column slice of the tile
         uint32_t* scr = reinterpret_cast<uint32_t*>(scr_base + ew * SCR_BYTES);
-        float* sbias = reinterpret_cast<float*>(scr + (G::TMA ? TMA_WARP_BYTES / 4 : 32 * SCR_STRIDE));  // [WCOLS]
+        float* sbias = reinterpret_cast<float*>(scr + (G::TMA ? TMA_WARP_BYTES / 4 : (G::PTMA ? 1024 : 32 * SCR_STRIDE)));  // [WCOLS]
         constexpr bool packed = EPI != EPI_F32 && EPI != EPI_F32_EMIT && EPI != EPI_F32_TMA;
         constexpr bool EMIT = EPI == EPI_F32_EMIT;
         constexpr bool LN = G::LN;
@@ -517,6 +520,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
                 uint32_t v[2][32];
                 ptx::tmem_ld_32x32(tbase, v[0]);
                 uint32_t* srow = scr + lane * SCR_STRIDE;
+                if constexpr (G::PTMA) {
+                    static_assert(!G::PTMA || NBLK == 2, "one 64-column staging tile per warp and tile");
+                    if (lane == 0) ptx::bulk_wait_read0();  // the previous tile's store has read the staging tile (long ago)
+                    __syncwarp();
+                }
 #pragma unroll
                 for (int blk = 0; blk < NBLK; ++blk) {
                     const int chunk = blk >> 1, hh = blk & 1;
@@ -554,10 +562,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
 #pragma unroll
                             for (int e = 0; e < 8; e += 2) gelu_fast2(f[e], f[e + 1]);
                         }
-                        *reinterpret_cast<uint4*>(srow + (hh * 4 + j) * 4) =
-                            make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
+                        if constexpr (G::PTMA) {
+                            // row-per-thread staging tile in the SWIZZLE_128B layout of the output tensor map
+                            *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(scr) + lane * 128 + (((hh * 4 + j) ^ (lane & 7)) << 4)) =
+                                make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
+                        } else {
+                            *reinterpret_cast<uint4*>(srow + (hh * 4 + j) * 4) =
+                                make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
+                        }
                     }
-                    if (hh == 1) {
+                    if constexpr (G::PTMA) {
+                        if (hh == 1) {
+                            ptx::fence_proxy_async_smem();
+                            __syncwarp();
+                            if (lane == 0 && ncol0 + chunk * 64 < p.N) {
+                                ptx::tma_store_3d(&tmO2, ptx::smem_u32(scr), ncol0 + chunk * 64, tile_ok ? trow0 : p.tpb * BM, b);
+                                ptx::bulk_commit();
+                            }
+                        }
+                    } else if (hh == 1) {
                         __syncwarp();
                         const int col = ncol0 + chunk * 64 + c8 * 8;
                         bf16* orow = p.out2 + ((long long)b * p.out2_bs + trow0 + rsub) * p.N + col;
@@ -692,7 +715,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         }
     }
 
-    if (G::TMA && warp >= 2 && lane == 0) ptx::bulk_wait0();  // outstanding TMA stores read this CTA's shared memory
+    if ((G::TMA || G::PTMA) && warp >= 2 && lane == 0) ptx::bulk_wait0();  // outstanding TMA stores read this CTA's shared memory
     ptx::tc_fence_before();
     if (NCTA == 2) ptx::cluster_sync(); else __syncthreads();
     if (warp == 1) {
@@ -773,6 +796,8 @@ void launch(const GemmProblem& g, cudaStream_t s) {
         g.A2 ? make_tmap_bf16_3d(g.A2, g.K2, g.Lr, g.nb, g.a2_bs ? g.a2_bs : g.Lr, BM, BK) : tmA1;
     const CUtensorMap tmB = make_tmap_bf16_3d(g.W16, K, g.N, 1, g.N, BN / NCTA, BK);
     CUtensorMap tmO32 = tmA1, tmO32b = tmA1, tmO2 = tmA1, tmO2b = tmA1;
+    if (EPI == EPI_LN_GELU_W16)
+        tmO2 = make_tmap_3d(g.out2, 2, g.N, g.Lr, g.nb, p.out2_bs, 32, 64, CU_TENSOR_MAP_SWIZZLE_128B);
     if (EPI == EPI_F32_TMA) {
         tmO32 = make_tmap_3d(g.out32, 4, g.N, g.Lr, g.nb, p.out32_bs, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B);
         if (g.out32b) tmO32b = make_tmap_3d(g.out32b, 4, g.N, g.Lr, g.nb, p.out32b_bs, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B);
