@@ -102,7 +102,7 @@ void convert_f32_bf16(const float* in, bf16* out, long long n, cudaStream_t s);
 void rowstats_convert(const float* x, bf16* out, float* stats, long long rows, int D, cudaStream_t s);
 void ln_rstd(const float* stats, float* rstd, long long rows, int D, cudaStream_t s);  // row sums -> 1 / sqrt(var + 1e-5)
 void fold_ln_weight(const float* W, const float* bias, const float* gamma, const float* beta, bf16* Wf, float* d, int N,
-                    int K, cudaStream_t s);
+                    int K, bool for_gelu, cudaStream_t s);
 constexpr int LN_PART = 128;  // columns per partial-sum slice (= accumulator columns per GEMM epilogue warp)
 void copy_rows(void* dst, int dst_bs, const void* src, int src_bs, int Lr, int nb, int row_bytes, cudaStream_t s);
 

@@ -193,7 +193,7 @@ void ln_rstd(const float* stats, float* rstd, long long rows, int D, cudaStream_
 // the output, below the bf16 rounding of the stored activation for any row whose mean is not many times its spread.)
 __global__ void __launch_bounds__(128) fold_ln_kernel(const float* __restrict__ W, const float* __restrict__ bias,
                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                      bf16* __restrict__ Wf, float* __restrict__ d, int K) {
+                                                      bf16* __restrict__ Wf, float* __restrict__ d, int K, float dscale) {
     const int n = blockIdx.x;
     float sm = 0.f, sd = 0.f;
     for (int k = threadIdx.x; k < K; k += blockDim.x) {
@@ -215,11 +215,12 @@ __global__ void __launch_bounds__(128) fold_ln_kernel(const float* __restrict__ 
     const float m = ((red[0][0] + red[0][1]) + (red[0][2] + red[0][3])) / (float)K;
     for (int k = threadIdx.x; k < K; k += blockDim.x)
         Wf[(size_t)n * K + k] = __float2bfloat16_rn(gamma[k] * W[(size_t)n * K + k] - m);
-    if (threadIdx.x == 0) d[n] = (bias ? bias[n] : 0.f) + ((red[1][0] + red[1][1]) + (red[1][2] + red[1][3]));
+    if (threadIdx.x == 0) d[n] = dscale * ((bias ? bias[n] : 0.f) + ((red[1][0] + red[1][1]) + (red[1][2] + red[1][3])));
 }
 void fold_ln_weight(const float* W, const float* bias, const float* gamma, const float* beta, bf16* Wf, float* d, int N,
-                    int K, cudaStream_t s) {
-    fold_ln_kernel<<<N, 128, 0, s>>>(W, bias, gamma, beta, Wf, d, K);
+                    int K, bool for_gelu, cudaStream_t s) {
+    // for_gelu: the consuming epilogue works on x / 2 (gelu_fast2_half in gemm_tc.cu): the folded bias is stored halved
+    fold_ln_kernel<<<N, 128, 0, s>>>(W, bias, gamma, beta, Wf, d, K, for_gelu ? 0.5f : 1.f);
     check_launch("fold_ln_weight");
 }
 

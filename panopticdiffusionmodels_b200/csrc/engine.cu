@@ -281,18 +281,18 @@ struct pdm_engine {
         if (skip) b.skip = lin(pre + "skip_linear.weight", pre + "skip_linear.bias", D, 2 * D);
         return b;
     }
-    FoldW fold(const std::string& key, const LinearW& l, const float* gamma, const float* beta, cudaStream_t s) {
+    FoldW fold(const std::string& key, const LinearW& l, const float* gamma, const float* beta, bool for_gelu, cudaStream_t s) {
         FoldW& f = folds[key];
         if (!f.w) {
             PDM_CHECK_CUDA(cudaMalloc(&f.w, (size_t)l.N * l.K * sizeof(bf16)));
             PDM_CHECK_CUDA(cudaMalloc(&f.d, (size_t)l.N * sizeof(float)));
         }
-        fold_ln_weight(l.w32, l.b, gamma, beta, f.w, f.d, l.N, l.K, s);
+        fold_ln_weight(l.w32, l.b, gamma, beta, f.w, f.d, l.N, l.K, for_gelu, s);
         return f;
     }
     void fold_block(const std::string& pre, BlockW& b, cudaStream_t s) {
-        b.qkv_f = fold(pre + "qkv", b.qkv, b.n1w, b.n1b, s);
-        b.fc1_f = fold(pre + "fc1", b.fc1, b.n2w, b.n2b, s);
+        b.qkv_f = fold(pre + "qkv", b.qkv, b.n1w, b.n1b, false, s);
+        b.fc1_f = fold(pre + "fc1", b.fc1, b.n2w, b.n2b, true, s);
     }
     void finalize(cudaStream_t s) {
         std::string missing;
@@ -1174,7 +1174,7 @@ int pdm_debug_ln_chain(const float* A, const float* W1, const float* b1, const f
         } else {
             rowstats_convert((const float*)x.p, (bf16*)xb.p, (float*)stats.p, M, D, s);
         }
-        fold_ln_weight(W2, b2, gamma, beta, (bf16*)wf.p, (float*)d.p, N, D, s);
+        fold_ln_weight(W2, b2, gamma, beta, (bf16*)wf.p, (float*)d.p, N, D, gelu != 0, s);
         GemmProblem g;
         g.A1 = xb.p; g.K1 = D; g.W16 = (const bf16*)wf.p; g.bias = (const float*)d.p;
         ln_rstd((const float*)stats.p, (float*)rs.p, M, D, s);

@@ -163,6 +163,34 @@ __device__ __forceinline__ void add2(float& x0, float& x1, float d0, float d1) {
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(x) : "l"(x), "l"(d));
     asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(x));
 }
+// gelu_fast2 on HALVED inputs: h = x / 2 comes straight out of the LayerNorm FMA (1/std and the folded bias are pre-scaled by
+// 1/2, exact in binary floating point), so the separate 0.5 * x multiply disappears; u' = h^2 = x^2 / 4 and the polynomial
+// coefficients carry the powers of two: x (a + b x^2 + c x^4) = h (2a + 8b u' + 32c u'^2).  Bit-identical to gelu_fast2(2h).
+__device__ __forceinline__ void gelu_fast2_half(float& h0, float& h1) {
+    uint64_t h, u, w, r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(h) : "f"(h0), "f"(h1));
+    asm("mul.rn.f32x2 %0, %1, %1;" : "=l"(u) : "l"(h));
+    float u0, u1;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(u0), "=f"(u1) : "l"(u));
+    u0 = fminf(u0, 16.f);
+    u1 = fminf(u1, 16.f);
+    asm("mov.b64 %0, {%1, %2};" : "=l"(u) : "f"(u0), "f"(u1));
+    uint64_t ca, cb, cc;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(cc) : "f"(32.f * -3.56580544e-04f));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(cb) : "f"(8.f * 3.70435562e-02f));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(ca) : "f"(2.f * 7.97452612e-01f));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(w) : "l"(u), "l"(cc), "l"(cb));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(w) : "l"(u), "l"(w), "l"(ca));
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(w) : "l"(w), "l"(h));
+    float w0, w1, t0, t1;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(w0), "=f"(w1) : "l"(w));
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(w0));
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(w1));
+    uint64_t t;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(t) : "f"(t0), "f"(t1));
+    asm("fma.rn.f32x2 %0, %1, %2, %1;" : "=l"(r) : "l"(h), "l"(t));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(h0), "=f"(h1) : "l"(r));
+}
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&v);
@@ -508,7 +536,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
                 // sums the producer of x left behind (read before the accumulator is waited for)
                 uint64_t rstd2 = 0;
                 if constexpr (LN) {
-                    asm("mov.b64 %0, {%1, %1};" : "=l"(rstd2) : "f"(rstd_next));
+                    // GELU forms: halved here (the folded bias is halved at finalize), see gelu_fast2_half
+                    asm("mov.b64 %0, {%1, %1};" : "=l"(rstd2) : "f"(G::GELU ? 0.5f * rstd_next : rstd_next));
                     rstd_next = load_rstd(tile + n_units);
                 }
                 __syncwarp();
@@ -558,7 +587,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
                                 add2(f[6], f[7], b1.z, b1.w);
                             }
                         }
-                        if (gelu) {
+                        if constexpr (LN && G::GELU) {
+#pragma unroll
+                            for (int e = 0; e < 8; e += 2) gelu_fast2_half(f[e], f[e + 1]);
+                        } else if (gelu) {
 #pragma unroll
                             for (int e = 0; e < 8; e += 2) gelu_fast2(f[e], f[e + 1]);
                         }
