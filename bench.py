@@ -298,7 +298,9 @@ def run_ours(a):
                 "flops_per_launch": gemm_flops / g_n, "share_of_step": round(g_ms / tot, 4), "traffic": gemm_traffic()}
 
     if rank == 0:
-        cb = None if a.no_cpu_baseline else cpu_eval_rate(kw, a.nfe, a.scale, steps=1, warmup=1)
+        # the CPU baseline is a rank-0, N = 1 measurement (under torchrun the host cores are shared by all ranks and
+        # OMP_NUM_THREADS is pinned to 1: the number would be meaningless)
+        cb = None if (a.no_cpu_baseline or world > 1) else cpu_eval_rate(kw, a.nfe, a.scale, steps=1, warmup=1)
         h2d = (h_ctx.numel() + h_empty.numel() + h_z.numel() + h_m.numel()) * 4
         d2h = (out_host_z.numel() + out_host_m.numel()) * 4
         line = {
