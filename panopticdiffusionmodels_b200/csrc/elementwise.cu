@@ -402,9 +402,10 @@ void embed_tokens(const EmbedArgs& a, cudaStream_t s) {
 // One warp = HEAD_T consecutive patches of one stream of one sample.  The (normalised) token rows live in registers
 // (lane owns float4 chunks lane + 32 i); every decoder weight row is read once per HEAD_T tokens, and the 32-lane partial
 // sums of 8 outputs are combined with a transposing butterfly (4 + 2 + 1 + 2 shuffles per token instead of 8 x 5).
-constexpr int HEAD_T = 4;
+// (4 tokens per warp for D <= 512; 2 for wider models, whose rows would otherwise take > 200 registers per thread)
 template <int NV>
 __global__ void __launch_bounds__(256) head_token_kernel(HeadArgs a) {
+    constexpr int HEAD_T = NV > 4 ? 2 : 4;
     const int g = a.S / a.p;
     const int P = g * g;
     const int gpr = (P + HEAD_T - 1) / HEAD_T;  // token groups per (stream, sample)
@@ -598,7 +599,8 @@ __global__ void __launch_bounds__(256) conv3x3_kernel(const float* __restrict__ 
 void head_decode(const HeadArgs& a, cudaStream_t s) {
     const int g = a.S / a.p;
     const int P = g * g;
-    const int nwarps = a.nb * ceil_div(P, HEAD_T) * ((a.m && !a.gt) ? 2 : 1);
+    const int head_t = ceil_div(a.D, 128) > 4 ? 2 : 4;  // = HEAD_T of the instantiation chosen below
+    const int nwarps = a.nb * ceil_div(P, head_t) * ((a.m && !a.gt) ? 2 : 1);
     PDM_REQUIRE(a.D % 4 == 0 && a.D <= 1024, "head: D must be a multiple of 4 and <= 1024");
     const int nv = ceil_div(a.D, 128);
     const int hgrid = ceil_div(nwarps, 8);
