@@ -174,7 +174,7 @@ def workload(a, kw, B):
 def run_ours(a):
     import torch
     import torch.distributed as dist
-    from oracle import uvit_oracle  # flops formula only (bench bookkeeping; not on the measured path)
+    from panopticdiffusionmodels_b200.flops import flops_per_forward
     from panopticdiffusionmodels_b200 import _lib
     from panopticdiffusionmodels_b200.libs.uvit_t2i import UViT
     from panopticdiffusionmodels_b200.sampling import JointSampler
@@ -257,7 +257,7 @@ def run_ours(a):
 
     samples = world * B * a.steps
     value = samples / (ms / 1e3)
-    F = uvit_oracle.flops_per_forward(dict(kw, clip_dim=768), with_mask=True)   # per sample per forward
+    F = flops_per_forward(dict(kw, clip_dim=768), with_mask=True)   # per sample per forward
     flops_step = 2 * a.nfe * F * B                                               # per GPU per step (cond + uncond)
     pk = peaks()
 
