@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PDM_ABI_VERSION 1
+#define PDM_ABI_VERSION 2
 
 /* precision modes of the network evaluation */
 #define PDM_PREC_BF16 0 /* bf16 operands on tcgen05 tensor cores, fp32 accumulate, fp32 residual stream */
@@ -43,8 +43,20 @@ extern "C" {
  *  [8] stage     0,1,2 : index of this evaluation inside its solver step
  *  [9] has_c     1 if the (X_j - X_0) term is present (stage > 0)
  *  [10] last     1 if this evaluation closes its solver step (output becomes the next step-start state)
- *  [11..15] reserved (0)
+ *  [11] A_msk    [12] split: when split == 1 the mask stream is the reference's enable_mask_opt=False pass-through,
+ *                m_out = A_msk * m_base + B_msk * P_0 (no difference term): the intermediate evaluations see the step-start
+ *                mask, the next step starts from the prediction itself (dpm_solver_pp.py:441-457, 536-557, 730-766)
+ *  [13..14] reserved (0)
+ *  [15] kind     0: singlestep record (above); 1: multistep record (layout: see pdm_multistep_update)
  */
+
+/* pdm_solver_plan: method / skip_type codes (dpm_solver_pp.py:927-930 `method`, `skip_type`) */
+#define PDM_METHOD_FAST 0        /* 'fast': singlestep orders 3,...,3,2 / 3,...,3,1 / 3,...,3,2,1 (dpm_solver_pp.py:386-395) */
+#define PDM_METHOD_SINGLESTEP 1  /* 'singlestep': steps // order updates of one order */
+#define PDM_METHOD_MULTISTEP 2   /* 'multistep': 2M / 3M with lower-order warm-up */
+#define PDM_SKIP_TIME_UNIFORM 0
+#define PDM_SKIP_LOGSNR 1
+#define PDM_SKIP_T2 2 /* 't2' (dpm_solver_pp.py:351-354); the reference's 10^7-point 'time_quadratic' search is not offered */
 
 typedef struct pdm_engine* pdm_handle;
 
@@ -103,7 +115,8 @@ int pdm_nnet_forward_ex(pdm_handle h, const float* x, const float* t, const floa
  *   eps_c/eps_u [B,4hw] (eps_u NULL -> no guidance), pm_c/pm_u [B,8hw] (NULL -> no mask stream),
  *   x_in  state the network was evaluated at; x_base step-start state (== x_in at stage 0);
  *   X0/P0 data-prediction history of stage 0 (written at stage 0, read later);
- *   x_out/m_out next state.  m_in is not needed (the mask "x0" is the prediction itself). */
+ *   x_out/m_out next state.  m_in is not needed (the mask "x0" is the prediction itself).
+ *   coef[12] != 0 selects the pass-through mask update m_out = coef[11] * m_base + coef[6] * P0 (see the record layout). */
 int pdm_cfg_update(const float* eps_c, const float* eps_u, const float* pm_c, const float* pm_u,
                    const float* x_in, const float* x_base, float* X0, float* x_out,
                    const float* m_base, float* P0, float* m_out,
@@ -121,6 +134,22 @@ int pdm_multistep_update(const float* eps_c, const float* eps_u, const float* pm
                          const float* P2, float* P0, float* m_out, const float* coef, float cfg_scale, int64_t n_img,
                          int64_t n_mask, void* stream);
 
+/* replaces: the host-side scalar work of DPM_Solver.sample -- NoiseScheduleVP('discrete', betas) (dpm_solver_pp.py:55-169,
+ * interpolate_fn :9-52), get_time_steps / get_orders_and_timesteps_for_singlestep_solver (:330-405) and the per-step
+ * coefficients of the 1S / 2S / 3S (:432-457, :511-557, :700-766) and 1 / 2M / 3M (:602-677, driver :995-1017) updates
+ * (data prediction, solver_type 'dpm_solver').  HOST function, no device work, no handle: fills `out_plan`
+ * [n_evals][PDM_PLAN_STRIDE] (one record per network evaluation) for pdm_sample.
+ *   betas [n_betas] HOST float32 (the discrete schedule, train_t2i_discrete.py:40-44, 504); steps = number of function
+ *   evaluations; order 1..3; eps = end time t_0 (1/N in the t2i path), T = start time (1.0);
+ *   mask_opt != 0: the mask stream follows the solver update (enable_mask_opt=True, the live path); 0: pass-through;
+ *   n_time: factor from continuous to model time (1000, train_t2i_discrete.py:508).
+ *   out_plan may be NULL to query *n_evals; cap_evals = capacity of out_plan in records.
+ * Agrees with the Python host planner (float32 torch ops = what the reference computes) to a few float32 ulp per
+ * coefficient (libm vs SLEEF transcendental rounding), see csrc/plan.cu. */
+int pdm_solver_plan(const float* betas, int32_t n_betas, int32_t steps, int32_t order, int32_t method, int32_t skip_type,
+                    float eps, float T, int32_t mask_opt, float n_time, float* out_plan, int32_t cap_evals,
+                    int32_t* n_evals);
+
 /* replaces: DPM_Solver.sample(method='fast') (dpm_solver_pp.py:1018-1044) driven by cfg_nnet
  * (train_t2i_discrete.py:387-439, 506-516): the whole denoising loop on the device.
  *   plan: HOST array [n_evals][PDM_PLAN_STRIDE] built by the host planner (solver scalars are data
@@ -128,6 +157,9 @@ int pdm_multistep_update(const float* eps_c, const float* eps_u, const float* pm
  *   ctx [B,T,clip]; empty_ctx [T,clip] (NULL -> no guidance, cfg_scale ignored);
  *   out_z [B,4,H,W]; out_pred_mask [B,8,H,W] = CFG'd mask prediction of the first evaluation of the
  *   last solver step (dpm_solver_pp.py:827,1044).
+ * A plan of multistep records (kind 1, pdm_solver_plan with PDM_METHOD_MULTISTEP) runs DPM-Solver++ 2M / 3M the same way:
+ * one network evaluation + ONE fused update kernel per step, the data-prediction history kept in the engine's workspace;
+ * out_pred_mask is then the mask prediction of the last evaluation.
  * use_graph != 0 captures the loop into a CUDA graph (cached per (B, n_evals, precision)). */
 int pdm_sample(pdm_handle h, const float* plan, int32_t n_evals, const float* z_init, const float* mask_init,
                const float* ctx, const float* empty_ctx, float cfg_scale, float* out_z, float* out_pred_mask,

@@ -274,7 +274,7 @@ def cfg_model(sd, cfg, context, empty_context, scale, dtype=F32, n_time=1000) ->
 
     def fn(x, t_cont, mask, gt=False):
         B = x.shape[0]
-        t = (torch.ones(B) * t_cont) * n_time
+        t = (torch.ones(B, device=x.device) * t_cont) * n_time
         ec = empty_context.unsqueeze(0).expand(B, -1, -1)
         if mask is None:
             c = uvit_oracle.uvit_forward(sd, cfg, x, t, context, None, dtype).float()

@@ -33,7 +33,7 @@ import torch.nn.functional as F
 def timestep_embedding(timesteps: torch.Tensor, dim: int, max_period: int = 10000) -> torch.Tensor:
     # libs/uvit_t2i.py:30-38 -- frequencies are always built in float32.
     half = dim // 2
-    freqs = torch.exp(-math.log(max_period) * torch.arange(0, half, dtype=torch.float32) / half)
+    freqs = torch.exp(-math.log(max_period) * torch.arange(0, half, dtype=torch.float32) / half).to(timesteps.device)
     args = timesteps[:, None].float() * freqs[None]
     emb = torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
     if dim % 2:
@@ -182,22 +182,3 @@ def uvit_forward(sd: Dict[str, torch.Tensor], cfg: dict, x: torch.Tensor, timest
     noise = _unpatchify(noise, in_ch)
     noise = F.conv2d(noise, sd["final_layer.weight"], sd["final_layer.bias"], padding=1)
     return noise if y is None else (noise, y)
-
-
-def flops_per_forward(cfg: dict, with_mask: bool = True) -> float:
-    """Algorithmic FLOPs per sample per forward."""
-    D, depth = cfg["embed_dim"], cfg["depth"]
-    P = (cfg["img_size"] // cfg["patch_size"]) ** 2
-    ext = 1 + cfg.get("num_clip_token", 77)
-    clip = cfg.get("clip_dim", 768)
-
-    def blocks(L):
-        return (depth + 1) * (24 * L * D * D + 4 * L * L * D) + (depth // 2) * 4 * L * D * D
-
-    f_io = 2 * P * D * (16 + 32) * 2 + 2 * (ext - 1) * clip * D + 18 * 4 * P * (16 + 64)
-    if not with_mask:
-        return blocks(ext + P) + f_io
-    if cfg.get("separate", False):
-        L1, L2 = ext + P, ext + 2 * P
-        return blocks(L1) + blocks(L2) + (depth + 1) * 2 * L1 * D * D + f_io
-    return blocks(ext + 2 * P) + f_io

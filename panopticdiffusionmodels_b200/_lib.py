@@ -16,7 +16,9 @@ PREC_BF16 = 0
 PREC_FP32 = 1
 FWD_GROUND_TRUTH = 1  # PDM_FWD_GROUND_TRUTH
 PLAN_STRIDE = 16
-ABI_VERSION = 1
+ABI_VERSION = 2
+METHOD_CODES = {"fast": 0, "singlestep": 1, "multistep": 2}
+SKIP_CODES = {"time_uniform": 0, "logSNR": 1, "t2": 2}
 
 
 class PdmConfig(C.Structure):
@@ -37,6 +39,8 @@ SIGNATURES = {
     "pdm_nnet_forward_ex": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P]),
     "pdm_cfg_update": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(C.c_float), C.c_float,
                                  C.c_int64, C.c_int64, _P]),
+    "pdm_solver_plan": (C.c_int, [C.POINTER(C.c_float), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float,
+                                  C.c_float, C.c_int32, C.c_float, C.POINTER(C.c_float), C.c_int32, C.POINTER(C.c_int32)]),
     "pdm_multistep_update": (C.c_int, [_P] * 14 + [C.POINTER(C.c_float), C.c_float, C.c_int64, C.c_int64, _P]),
     "pdm_sample": (C.c_int, [_P, C.POINTER(C.c_float), C.c_int32, _P, _P, _P, _P, C.c_float, _P, _P, C.c_int32,
                              C.c_int32, C.c_int32, _P]),

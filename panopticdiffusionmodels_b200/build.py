@@ -16,9 +16,10 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "build")
-LIB = os.path.join(HERE, "libpdm.so")
-SOURCES = ["elementwise.cu", "gemm_simt.cu", "gemm_tc.cu", "attention_simt.cu", "attention_tc2.cu", "attention_tc3.cu", "engine.cu"]
+TAG = os.environ.get("PDM_BUILD_TAG", "")  # development: a second library (e.g. a -DPDM_ATTN_TRACE build) next to the product one
+OBJ = os.path.join(HERE, "build" + TAG)
+LIB = os.path.join(HERE, f"libpdm{TAG}.so")
+SOURCES = ["elementwise.cu", "gemm_simt.cu", "gemm_tc.cu", "attention_simt.cu", "attention_tc3.cu", "plan.cu", "engine.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",

@@ -1,6 +1,9 @@
-"""The four MSCOCO U-ViT t2i configurations BASELINE.json names, with the same keys/values as the
-reference's ``configs/mscoco_uvit_{small,mid,large,small_512}.py`` (``get_config()`` -> ConfigDict).
-``load_config_file`` loads a reference-style config *file* unchanged (ml_collections shim)."""
+"""The four MSCOCO U-ViT t2i configurations BASELINE.json names as one table (``get_config()`` -> ConfigDict).  Every key
+of the reference's ``configs/mscoco_uvit_{small,mid,large,small_512}.py`` is present with the reference's value, except the
+three machine-specific absolute paths (``dataset.path``, ``sample.path`` and the small config's ``pretrained``), which are
+relative / ``None`` here (``tests/test_host_cpu.py::test_config_table_matches_reference_files`` pins this against
+``tests/golden/reference_configs.json``).  ``load_config_file`` loads a reference-style config *file* unchanged
+(ml_collections shim) when a user has one."""
 from __future__ import annotations
 
 import importlib.util
@@ -27,8 +30,8 @@ def get_config(name: str) -> ConfigDict:
     c.seed = 1234
     c.z_shape = (4, img, img)
     c.autoencoder = ConfigDict(dict(pretrained_path="assets/stable-diffusion/autoencoder_kl.pth", scale_factor=0.23010))
-    c.train = ConfigDict(dict(n_steps=2000000 if name == "mscoco_uvit_small" else 1000000, batch_size=train_bs,
-                              log_interval=20 if name == "mscoco_uvit_small" else 10, eval_interval=5000,
+    c.train = ConfigDict(dict(n_steps=2000000 if name in ("mscoco_uvit_small", "mscoco_uvit_small_512") else 1000000, batch_size=train_bs,
+                              log_interval=20 if name in ("mscoco_uvit_small", "mscoco_uvit_mid") else 10, eval_interval=5000,
                               save_interval=50000))
     c.optimizer = ConfigDict(dict(name="adamw", lr=0.0002, weight_decay=0.03, betas=(0.9, 0.9)))
     c.lr_scheduler = ConfigDict(dict(name="customized", warmup_steps=5000))

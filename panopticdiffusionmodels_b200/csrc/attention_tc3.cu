@@ -34,16 +34,6 @@ CUtensorMap make_tmap_bf16_3d(const void* ptr, long long K, long long rows, long
                               int box_rows, int box_k);
 namespace {
 
-int sm_count() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        PDM_CHECK_CUDA(cudaGetDevice(&dev));
-        PDM_CHECK_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
-    }
-    return n;
-}
-
 constexpr int QT = 128, KT = 128, HD = 64;
 constexpr int TILE_BYTES = 128 * HD * 2;  // 16 KB
 constexpr int NSLOT = 5;                  // K/V ring slots, (K tile | V tile) each
@@ -54,6 +44,10 @@ constexpr int THREADS = 384;  // warps 0-7 softmax, 8 TMA, 9 P.V, 10 Q.K^T, 11 i
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t S_COL = 0, P_COL = 256, O_COL = 384;  // + t * {128, 64, 64}
 constexpr float RESCALE_LOG2 = 8.f;
+#ifndef PDM_ATTN_LOCKSTEP
+#define PDM_ATTN_LOCKSTEP 0  // development switch (measured 0.79x: DESIGN.md, "tried and dropped")
+#endif
+constexpr bool LOCKSTEP = PDM_ATTN_LOCKSTEP != 0;
 
 __device__ __forceinline__ float ex2(float x) {
     float y;
@@ -163,8 +157,12 @@ __device__ __forceinline__ void trace_ev(int ev, uint32_t n, int& cnt) {
     }
 }
 #define TRACE(ev, n) trace_ev(ev, n, trace_cnt)
+#define TRACE_PARAM , int& trace_cnt
+#define TRACE_ARG , trace_cnt
 #else
 #define TRACE(ev, n)
+#define TRACE_PARAM
+#define TRACE_ARG
 #endif
 
 // exp2 on the FMA pipe: Cody-Waite split x = n + f with the round-to-nearest magic-number add, 2^f on [-0.5, 0.5] by a
@@ -198,7 +196,7 @@ __device__ __forceinline__ void exp2_poly2(float a0, float a1, float& p0, float&
 template <int NCH, bool MASK>
 __device__ __forceinline__ void softmax_tile(uint32_t s_addr, uint32_t p_addr, uint32_t o_addr, int nvalid, bool first,
                                              bool wait_prev, float& m_ref, float& l, uint32_t s_free_bar,
-                                             uint32_t o_full_bar, uint32_t o_full_parity, int lane) {
+                                             uint32_t o_full_bar, uint32_t o_full_parity, int lane, bool lockstep TRACE_PARAM) {
     const float cs = 0.125f * 1.4426950408889634f;  // softmax scale * log2(e)
     uint32_t s[NCH][32];
     // (loading in two halves, to run the row max of the first under the TMEM load of the second, measured 1.5 % slower)
@@ -230,6 +228,7 @@ __device__ __forceinline__ void softmax_tile(uint32_t s_addr, uint32_t p_addr, u
     ptx::tc_fence_before();
     __syncwarp();
     if (lane == 0) ptx::mbar_arrive(s_free_bar);  // the next Q.K^T of this tile slot may overwrite S now
+    TRACE(6, 0);
     if (MASK && NCH != H1) mask_tail();
 #pragma unroll
     for (int c = H1; c < NCH; ++c) row_max(c);
@@ -237,9 +236,17 @@ __device__ __forceinline__ void softmax_tile(uint32_t s_addr, uint32_t p_addr, u
     if (wait_prev) {
         // the previous P.V of this slot read P_t and wrote O_t: it must be complete before either is touched.  (Waiting
         // later, just before the first P store, measured 6 % slower: the wait splits the exp2 schedule.)
+        TRACE(7, 0);
         ptx::mbar_wait(o_full_bar, o_full_parity);
         ptx::tc_fence_after();
     }
+    // LOCKSTEP: both softmax warpgroups enter their exp2 phase together.  A scheduler hosts one warp of each warpgroup; left
+    // alone the two drift into ANTI-phase -- one in its exp2 phase (issuing at its full single-warp rate, HOLD bits keeping
+    // the issue port), the other crawling through its barrier / TMEM-load / row-max code at a third of its speed -- and the
+    // MUFU pipe only ever serves one warp (clock64 trace: exp 1360 clk, everything else 1680 clk per step, 50 % MUFU busy).
+    // In phase, the exp2 phases share the MUFU pipe and the bookkeeping phases run unstarved side by side.
+    if (lockstep) asm volatile("bar.sync 1, 256;" ::: "memory");
+    TRACE(8, 0);
     if (first) {
         m_ref = mx;
     } else if (__any_sync(0xffffffffu, (mx - m_ref) * cs > RESCALE_LOG2)) {
@@ -552,17 +559,18 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict
                     // before P_t is rewritten / O_t rescaled, the previous P.V of this slot must be complete: the previous
                     // key tile's (j > 0) or the previous item's last one (same phase the deferred epilogue waits for)
                     const bool wait_prev = j > 0 || pend.any;
+                    const bool lockstep = LOCKSTEP && nt == 2;  // both warpgroups walk this item
                     const uint32_t ofp = (steps - 1) & 1;
                     if (live) {
                         if (j < nkv - 1) {
-                            softmax_tile<4, false>(s_addr, p_addr, o_addr, KT, j == 0, wait_prev, m_ref, l, b_s_free, b_o_full, ofp, lane);
+                            softmax_tile<4, false>(s_addr, p_addr, o_addr, KT, j == 0, wait_prev, m_ref, l, b_s_free, b_o_full, ofp, lane, lockstep TRACE_ARG);
                         } else {
                             const int nv = sh.last_valid;
                             switch (nch_last) {
-                                case 1: softmax_tile<1, true>(s_addr, p_addr, o_addr, nv, j == 0, wait_prev, m_ref, l, b_s_free, b_o_full, ofp, lane); break;
-                                case 2: softmax_tile<2, true>(s_addr, p_addr, o_addr, nv, j == 0, wait_prev, m_ref, l, b_s_free, b_o_full, ofp, lane); break;
-                                case 3: softmax_tile<3, true>(s_addr, p_addr, o_addr, nv, j == 0, wait_prev, m_ref, l, b_s_free, b_o_full, ofp, lane); break;
-                                default: softmax_tile<4, true>(s_addr, p_addr, o_addr, nv, j == 0, wait_prev, m_ref, l, b_s_free, b_o_full, ofp, lane); break;
+                                case 1: softmax_tile<1, true>(s_addr, p_addr, o_addr, nv, j == 0, wait_prev, m_ref, l, b_s_free, b_o_full, ofp, lane, lockstep TRACE_ARG); break;
+                                case 2: softmax_tile<2, true>(s_addr, p_addr, o_addr, nv, j == 0, wait_prev, m_ref, l, b_s_free, b_o_full, ofp, lane, lockstep TRACE_ARG); break;
+                                case 3: softmax_tile<3, true>(s_addr, p_addr, o_addr, nv, j == 0, wait_prev, m_ref, l, b_s_free, b_o_full, ofp, lane, lockstep TRACE_ARG); break;
+                                default: softmax_tile<4, true>(s_addr, p_addr, o_addr, nv, j == 0, wait_prev, m_ref, l, b_s_free, b_o_full, ofp, lane, lockstep TRACE_ARG); break;
                             }
                         }
                         TRACE(2, steps);
@@ -570,6 +578,7 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict
                     } else {
                         if (lane == 0) ptx::mbar_arrive(b_s_free);
                         if (wait_prev) ptx::mbar_wait(b_o_full, ofp);  // keep in step with o_full
+                        if (lockstep) asm volatile("bar.sync 1, 256;" ::: "memory");
                     }
                     ptx::tc_fence_before();
                     __syncwarp();
@@ -604,14 +613,11 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict
 
 }  // namespace
 
-void attention_tc3(const bf16* qkv, bf16* out, int nb, int L, int H, cudaStream_t s) {
+void attention_tc_bf16(const bf16* qkv, bf16* out, int nb, int L, int H, cudaStream_t s) {
     const int D = H * HD;
     const CUtensorMap tm = make_tmap_bf16_3d(qkv, 3LL * D, L, nb, L, 128, HD);
-    static bool attr_set = false;
-    if (!attr_set) {
-        PDM_CHECK_CUDA(cudaFuncSetAttribute(attention_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        attr_set = true;
-    }
+    static std::atomic<bool> attr_set[MAX_DEVICES];
+    ensure_dyn_smem(attention_tc3_kernel, SMEM_BYTES, attr_set);
     Shape sh;
     sh.L = L;
     sh.H = H;

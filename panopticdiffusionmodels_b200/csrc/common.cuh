@@ -38,6 +38,35 @@ inline void check_launch(const char* what) {
     if (e != cudaSuccess) throw Error(std::string(what) + " launch failed: " + cudaGetErrorString(e));
 }
 
+// Per-device state: function attributes (the opt-in for > 48 KB of dynamic shared memory) and device properties belong to
+// a device / context, not to the process -- a module moved to a second GPU in the same process needs them again.
+constexpr int MAX_DEVICES = 64;
+inline int current_device() {
+    int dev = 0;
+    PDM_CHECK_CUDA(cudaGetDevice(&dev));
+    PDM_REQUIRE(dev >= 0 && dev < MAX_DEVICES, "device ordinal out of range");
+    return dev;
+}
+inline int sm_count() {
+    static std::atomic<int> n[MAX_DEVICES];
+    const int dev = current_device();
+    int v = n[dev].load(std::memory_order_relaxed);
+    if (v == 0) {
+        PDM_CHECK_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev));
+        n[dev].store(v, std::memory_order_relaxed);
+    }
+    return v;
+}
+// Opt a kernel in to `bytes` of dynamic shared memory once per device.  `done` is a per-kernel flag array.
+template <typename K>
+inline void ensure_dyn_smem(K kernel, int bytes, std::atomic<bool>* done) {
+    const int dev = current_device();
+    if (!done[dev].load(std::memory_order_acquire)) {
+        PDM_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        done[dev].store(true, std::memory_order_release);
+    }
+}
+
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
 
@@ -170,7 +199,9 @@ struct UpdateArgs {
     float* P0;
     float* m_out;
     float alpha, sigma, A, B_img, C_img, B_msk, C_msk, scale;
+    float A_msk = 0.f;   // mask_plain: m_out = A_msk * m_base + B_msk * P0 (enable_mask_opt=False pass-through)
     int stage, has_c;
+    int mask_plain = 0;
     long long n_img, n_mask;
 };
 void cfg_solver_update(const UpdateArgs& a, cudaStream_t s);
@@ -195,6 +226,11 @@ struct MultistepArgs {
     long long n_img, n_mask;
 };
 void multistep_update(const MultistepArgs& a, cudaStream_t s);
+
+// host planner (plan.cu)
+int solver_plan(const float* betas, int n_betas, int steps, int order, int method, int skip_type, float eps, float T,
+                int mask_opt, float n_time, float* out, int cap, int* n_evals);
+const char* plan_last_error();
 
 void bits2int(const float* pm, int32_t* labels, int B, int nbits, int hw, cudaStream_t s);
 void int2bits(const int32_t* ids, float* bits, int B, int nbits, int hw, cudaStream_t s);

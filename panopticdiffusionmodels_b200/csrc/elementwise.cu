@@ -695,11 +695,14 @@ __global__ void __launch_bounds__(256) update_kernel(UpdateArgs a) {
                 p0 = reinterpret_cast<const float4*>(a.P0)[j];
             }
             const float4 mb = __ldg(reinterpret_cast<const float4*>(a.m_base) + j);
+            // pass-through stream (enable_mask_opt=False): its own A, no difference term
+            const float Am = a.mask_plain ? a.A_msk : a.A;
+            const int hc = a.mask_plain ? 0 : a.has_c;
             float4 o;
-            o.x = lin_update(mb.x, p0.x, P.x, a.A, a.B_msk, a.C_msk, a.has_c);
-            o.y = lin_update(mb.y, p0.y, P.y, a.A, a.B_msk, a.C_msk, a.has_c);
-            o.z = lin_update(mb.z, p0.z, P.z, a.A, a.B_msk, a.C_msk, a.has_c);
-            o.w = lin_update(mb.w, p0.w, P.w, a.A, a.B_msk, a.C_msk, a.has_c);
+            o.x = lin_update(mb.x, p0.x, P.x, Am, a.B_msk, a.C_msk, hc);
+            o.y = lin_update(mb.y, p0.y, P.y, Am, a.B_msk, a.C_msk, hc);
+            o.z = lin_update(mb.z, p0.z, P.z, Am, a.B_msk, a.C_msk, hc);
+            o.w = lin_update(mb.w, p0.w, P.w, Am, a.B_msk, a.C_msk, hc);
             reinterpret_cast<float4*>(a.m_out)[j] = o;
         }
     }

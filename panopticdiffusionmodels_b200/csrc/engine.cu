@@ -87,6 +87,7 @@ struct Workspace {
     float *xbase = nullptr, *xin = nullptr, *X0 = nullptr;
     float *mbase = nullptr, *min_ = nullptr, *P0 = nullptr;
     float *nz = nullptr, *ny = nullptr;
+    float *X1 = nullptr, *X2 = nullptr, *P1 = nullptr, *P2 = nullptr;  // 2M / 3M data-prediction history (ring with X0 / P0)
 };
 
 struct GraphEntry {
@@ -382,6 +383,10 @@ struct pdm_engine {
         w.P0 = (float*)a.take(w.nb * msk * 4);
         w.nz = (float*)a.take(w.nb * img * 4);
         w.ny = (float*)a.take(w.nb * msk * 4);
+        w.X1 = (float*)a.take(w.nb * img * 4);
+        w.X2 = (float*)a.take(w.nb * img * 4);
+        w.P1 = (float*)a.take(w.nb * msk * 4);
+        w.P2 = (float*)a.take(w.nb * msk * 4);
     }
     size_t workspace_bytes(int nb, int prec, bool with_mask) const {
         Workspace w;
@@ -771,6 +776,10 @@ struct pdm_engine {
         const int nb = cfg_on ? 2 * B : B;
         const long long n_img = (long long)B * C * S * S, n_msk = has_mask ? (long long)B * Cm * S * S : 0;
         compute_ctxtok(ws, nb, prec, s);
+        if (plan[15] != 0.f) {
+            enqueue_multistep(ws, plan, n_evals, B, has_mask, cfg_on, scale, prec, s);
+            return;
+        }
         for (int k = 0; k < n_evals; ++k) {
             const float* r = plan + (size_t)k * PDM_PLAN_STRIDE;
             const int stage = (int)r[8];
@@ -785,10 +794,49 @@ struct pdm_engine {
             u.x_in = xin; u.x_base = ws.xbase; u.X0 = ws.X0; u.x_out = last ? ws.xbase : ws.xin;
             u.m_base = ws.mbase; u.P0 = ws.P0; u.m_out = last ? ws.mbase : ws.min_;
             u.alpha = r[1]; u.sigma = r[2]; u.A = r[3]; u.B_img = r[4]; u.C_img = r[5]; u.B_msk = r[6]; u.C_msk = r[7];
+            u.A_msk = r[11]; u.mask_plain = r[12] != 0.f ? 1 : 0;
             u.scale = scale; u.stage = stage; u.has_c = r[9] != 0.f ? 1 : 0;
             u.n_img = n_img; u.n_mask = n_msk;
             cfg_solver_update(u, s);
         }
+    }
+
+    // DPM-Solver++ 2M / 3M (dpm_solver_pp.py:602-677, driver :995-1017 repaired): one network evaluation and ONE fused
+    // update kernel per step.  State ping-pongs between (xbase, xin) / (mbase, min_); the data predictions live in a ring
+    // of three buffers.  Ends with the result in the canonical output buffers (xbase, P0) that sample() copies out.
+    void enqueue_multistep(Workspace& ws, const float* plan, int n_evals, int B, bool has_mask, bool cfg_on, float scale,
+                           int prec, cudaStream_t s) {
+        const int nb = cfg_on ? 2 * B : B;
+        const long long n_img = (long long)B * C * S * S, n_msk = has_mask ? (long long)B * Cm * S * S : 0;
+        float* xs[2] = {ws.xbase, ws.xin};
+        float* ms[2] = {ws.mbase, ws.min_};
+        float* Xh[3] = {ws.X0, ws.X1, ws.X2};
+        float* Ph[3] = {ws.P0, ws.P1, ws.P2};
+        for (int k = 0; k < n_evals; ++k) {
+            const float* r = plan + (size_t)k * PDM_PLAN_STRIDE;
+            PDM_REQUIRE(r[15] != 0.f, "pdm_sample: a plan must not mix singlestep and multistep records");
+            const int order = (int)r[11];
+            PDM_REQUIRE(order >= 1 && order <= 3 && order <= k + 1, "pdm_sample: bad multistep order in plan");
+            float* cur = xs[k & 1];
+            float* nxt = xs[(k + 1) & 1];
+            float* mcur = has_mask ? ms[k & 1] : nullptr;
+            forward(ws, cur, mcur, B, nb, nullptr, r[0], ws.nz, has_mask ? ws.ny : nullptr, prec, s);
+            Scope sc(this, "cfg_solver_update", s);
+            MultistepArgs a;
+            a.eps_c = ws.nz; a.eps_u = cfg_on ? ws.nz + n_img : nullptr;
+            a.pm_c = has_mask ? ws.ny : nullptr; a.pm_u = (has_mask && cfg_on) ? ws.ny + n_msk : nullptr;
+            a.x = cur; a.X0 = Xh[k % 3]; a.X1 = Xh[(k + 2) % 3]; a.X2 = Xh[(k + 1) % 3]; a.x_out = nxt;
+            a.m = mcur; a.P0 = Ph[k % 3]; a.P1 = Ph[(k + 2) % 3]; a.P2 = Ph[(k + 1) % 3];
+            a.m_out = has_mask ? ms[(k + 1) & 1] : nullptr;
+            a.alpha = r[1]; a.sigma = r[2]; a.A = r[3]; a.B = r[4]; a.C1 = r[5]; a.C2 = r[6];
+            a.inv_r0 = r[7]; a.inv_r1 = r[8]; a.q = r[9]; a.inv_r01 = r[10]; a.order = order; a.halfB = r[12];
+            a.scale = scale; a.n_img = n_img; a.n_mask = n_msk;
+            multistep_update(a, s);
+        }
+        float* fin = xs[n_evals & 1];
+        if (fin != ws.xbase) PDM_CHECK_CUDA(cudaMemcpyAsync(ws.xbase, fin, n_img * 4, cudaMemcpyDeviceToDevice, s));
+        float* pfin = Ph[(n_evals - 1) % 3];
+        if (has_mask && pfin != ws.P0) PDM_CHECK_CUDA(cudaMemcpyAsync(ws.P0, pfin, n_msk * 4, cudaMemcpyDeviceToDevice, s));
     }
 
     void sample(const float* plan, int n_evals, const float* z_init, const float* mask_init, const float* ctx,
@@ -1014,6 +1062,7 @@ int pdm_cfg_update(const float* eps_c, const float* eps_u, const float* pm_c, co
         u.alpha = coef[1]; u.sigma = coef[2]; u.A = coef[3]; u.B_img = coef[4]; u.C_img = coef[5];
         u.B_msk = coef[6]; u.C_msk = coef[7]; u.scale = cfg_scale;
         u.stage = (int)coef[8]; u.has_c = coef[9] != 0.f ? 1 : 0;
+        u.A_msk = coef[11]; u.mask_plain = coef[12] != 0.f ? 1 : 0;
         u.n_img = n_img; u.n_mask = pm_c ? n_mask : 0;
         cfg_solver_update(u, (cudaStream_t)stream);
     });
@@ -1028,6 +1077,15 @@ int pdm_sample(pdm_handle h, const float* plan, int32_t n_evals, const float* z_
         h->sample(plan, n_evals, z_init, mask_init, ctx, empty_ctx, cfg_scale, out_z, out_pred_mask, B, precision,
                   use_graph != 0, (cudaStream_t)stream);
     });
+}
+
+int pdm_solver_plan(const float* betas, int32_t n_betas, int32_t steps, int32_t order, int32_t method, int32_t skip_type,
+                    float eps, float T, int32_t mask_opt, float n_time, float* out_plan, int32_t cap_evals,
+                    int32_t* n_evals) {
+    const int rc = solver_plan(betas, n_betas, steps, order, method, skip_type, eps, T, mask_opt, n_time, out_plan, cap_evals,
+                               n_evals);
+    if (rc) g_last_error = plan_last_error();
+    return rc;
 }
 
 int pdm_multistep_update(const float* eps_c, const float* eps_u, const float* pm_c, const float* pm_u, const float* x,

@@ -780,16 +780,6 @@ typedef std::tuple<const void*, long long, long long, long long, long long, int,
 std::map<MapKey, CUtensorMap> g_map_cache;
 std::mutex g_map_mutex;
 
-int num_sms() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        PDM_CHECK_CUDA(cudaGetDevice(&dev));
-        PDM_CHECK_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
-    }
-    return n;
-}
-
 template <int NCTA, int EPI>
 void launch(const GemmProblem& g, cudaStream_t s) {
     const int K2 = g.A2 ? g.K2 : 0;
@@ -836,13 +826,9 @@ void launch(const GemmProblem& g, cudaStream_t s) {
         if (g.out2) tmO2 = make_tmap_3d(g.out2, 2, g.N, g.Lr, g.nb, p.out2_bs, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
         if (g.out2b) tmO2b = make_tmap_3d(g.out2b, 2, g.N, g.Lr, g.nb, p.out2b_bs, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
     }
-    static bool attr_set = false;
-    if (!attr_set) {
-        PDM_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<NCTA, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            Cfg<NCTA, EPI>::SMEM_BYTES));
-        attr_set = true;
-    }
-    const int units = std::max(1, std::min(p.total_tiles, num_sms() / NCTA));
+    static std::atomic<bool> attr_set[MAX_DEVICES];
+    ensure_dyn_smem(gemm_tc_kernel<NCTA, EPI>, Cfg<NCTA, EPI>::SMEM_BYTES, attr_set);
+    const int units = std::max(1, std::min(p.total_tiles, sm_count() / NCTA));
     gemm_tc_kernel<NCTA, EPI><<<NCTA * units, Geo<EPI>::THREADS, Cfg<NCTA, EPI>::SMEM_BYTES, s>>>(tmA1, tmA2, tmB, tmO32, tmO32b, tmO2, tmO2b, p);
     check_launch("gemm_tc");
 }

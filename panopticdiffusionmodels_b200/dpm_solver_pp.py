@@ -234,6 +234,21 @@ def build_plan(ns: NoiseScheduleVP, steps: int, order: int = 3, eps: float = 1e-
     return np.asarray(recs, dtype=np.float32).reshape(-1, PLAN_STRIDE)
 
 
+def build_plan_c(betas, steps: int, order: int = 3, eps: float = 1e-3, T: float = 1.0, skip_type: str = "time_uniform",
+                 method: str = "fast", mask_opt: bool = True, n_time: float = 1000.0) -> np.ndarray:
+    """The same table from the C ABI's host planner (``pdm_solver_plan``, csrc/plan.cu) -- what a non-Python consumer of
+    libpdm.so calls.  Agrees with ``build_plan`` / ``build_multistep_plan`` to a few float32 ulp (libm vs SLEEF rounding)."""
+    L = _lib.lib()
+    b = np.ascontiguousarray(torch.as_tensor(betas).detach().float().cpu().numpy(), dtype=np.float32)
+    n = C.c_int32(0)
+    args = (b.ctypes.data_as(C.POINTER(C.c_float)), b.size, steps, order, _lib.METHOD_CODES[method], _lib.SKIP_CODES[skip_type],
+            float(eps), float(T), 1 if mask_opt else 0, float(n_time))
+    _lib.check(L.pdm_solver_plan(*args, None, 0, C.byref(n)))
+    out = np.zeros((n.value, PLAN_STRIDE), dtype=np.float32)
+    _lib.check(L.pdm_solver_plan(*args, out.ctypes.data_as(C.POINTER(C.c_float)), n.value, C.byref(n)))
+    return out
+
+
 class DPM_Solver:
     def __init__(self, model_fn, noise_schedule, predict_x0=False, thresholding=False, max_val=1.0, n_time=1000.0):
         """``model_fn(x, t_continuous, panoptic=, mask_token=, use_ground_truth=, enable_panoptic=) -> (noise, pred_mask)``
@@ -279,21 +294,24 @@ class DPM_Solver:
             raise RuntimeError("DPM_Solver (libpdm) has no CPU path: x must be a CUDA tensor")
         plan = build_plan(self.noise_schedule, steps, order, eps, T, skip_type, method,
                           mask_opt=bool(enable_mask_opt) or mask_token is None, n_time=self.n_time)
-        fast = (getattr(self.model, "_pdm_fast_path", False) and not use_ground_truth and not use_twophases
-                and not (mask_token is not None and not enable_mask_opt))  # pass-through encodings need slot 11
+        fast = getattr(self.model, "_pdm_fast_path", False) and not use_ground_truth and not use_twophases
         if fast:
             return self.model.run_plan(x, mask_token, plan, use_graph=self.use_graph)
         x, pred_mask, mask_t = self._sample_callback(x, mask_token, plan, enable_panoptic, use_ground_truth)
-        if use_twophases and mask_token is not None:
+        if use_twophases:
             # phase two (dpm_solver_pp.py:1071-1075): the same time grid again, starting from the phase-one image, with the
-            # phase-one mask held fixed and fed to the network as ground truth; the returned pred_mask is phase one's
+            # phase-one mask held fixed and fed to the network as ground truth (the reference runs this pass whether or not
+            # there is a mask stream); the returned pred_mask is phase one's
             plan2 = build_plan(self.noise_schedule, steps, order, eps, T, skip_type, method, mask_opt=False, n_time=self.n_time)
             x, _, _ = self._sample_callback(x, mask_t, plan2, True, True)
         return x, pred_mask
 
-    # ---- generic model_fn: Python loop, fused K12 kernel per evaluation ----------------------------
+    # ---- generic model_fn: Python loop, ONE fused K12 kernel per evaluation ----------------------------
     @torch.no_grad()
     def _sample_callback(self, x, mask_token, plan, enable_panoptic, use_ground_truth=False):
+        """Reference callback semantics (dpm_solver_pp.py:310-328) for an arbitrary ``model_fn``.  A model that offers
+        ``eval_pair`` (our CFGModel) hands back the un-combined cond / uncond outputs so that the guidance combine stays
+        inside the update kernel here as well."""
         L = _lib.lib()
         dev = x.device
         f32 = dict(device=dev, dtype=torch.float32)
@@ -308,34 +326,27 @@ class DPM_Solver:
             mbase = min_ = P0 = None
         B = x.shape[0]
         pred_mask = mask_token
+        pair = getattr(self.model, "eval_pair", None)
         with torch.cuda.device(dev):
             for rec in plan:
                 stage, last = int(rec[8]), rec[10] != 0
                 cur_x = xbase if stage == 0 else xin
                 cur_m = (mbase if stage == 0 else min_) if has_mask else None
                 t_cont = torch.full((B,), float(rec[0]) / self.n_time, **f32)
-                noise, pm = self.model(cur_x, t_cont, panoptic=pred_mask, mask_token=cur_m,
-                                       use_ground_truth=use_ground_truth, enable_panoptic=enable_panoptic)
-                noise = noise.to(**f32).contiguous()
-                pm = pm.to(**f32).contiguous() if (has_mask and pm is not None) else None
-                coef = np.array(rec, dtype=np.float32)
-                m_out = (mbase if last else min_) if has_mask else None
-                if has_mask and rec[12] != 0:
-                    # pass-through mask stream (enable_mask_opt=False): m_out = A_msk*m + B_msk*P0, done in torch
-                    coef_img = coef.copy()
-                    _lib.check(L.pdm_cfg_update(_lib.ptr(noise), None, None, None, _lib.ptr(cur_x), _lib.ptr(xbase),
-                                                _lib.ptr(X0), _lib.ptr(xbase if last else xin), None, None, None,
-                                                coef_img.ctypes.data_as(C.POINTER(C.c_float)), 0.0, xbase.numel(), 0,
-                                                _lib.current_stream()))
-                    if stage == 0:
-                        P0.copy_(pm)
-                    m_out.copy_(mbase * float(rec[11]) + P0 * float(rec[6]))
+                if pair is not None:
+                    ec, eu, pc, pu, scale = pair(cur_x, t_cont, mask_token=cur_m, use_ground_truth=use_ground_truth)
                 else:
-                    _lib.check(L.pdm_cfg_update(
-                        _lib.ptr(noise), None, _lib.ptr(pm), None, _lib.ptr(cur_x), _lib.ptr(xbase), _lib.ptr(X0),
-                        _lib.ptr(xbase if last else xin), _lib.ptr(mbase), _lib.ptr(P0), _lib.ptr(m_out),
-                        coef.ctypes.data_as(C.POINTER(C.c_float)), 0.0, xbase.numel(),
-                        mbase.numel() if has_mask else 0, _lib.current_stream()))
+                    noise, pm = self.model(cur_x, t_cont, panoptic=pred_mask, mask_token=cur_m,
+                                           use_ground_truth=use_ground_truth, enable_panoptic=enable_panoptic)
+                    ec, eu, scale = noise.to(**f32).contiguous(), None, 0.0
+                    pc, pu = (pm.to(**f32).contiguous() if (has_mask and pm is not None) else None), None
+                coef = np.ascontiguousarray(rec, dtype=np.float32)
+                m_out = (mbase if last else min_) if has_mask else None
+                _lib.check(L.pdm_cfg_update(
+                    _lib.ptr(ec), _lib.ptr(eu), _lib.ptr(pc), _lib.ptr(pu), _lib.ptr(cur_x), _lib.ptr(xbase), _lib.ptr(X0),
+                    _lib.ptr(xbase if last else xin), _lib.ptr(mbase), _lib.ptr(P0), _lib.ptr(m_out),
+                    coef.ctypes.data_as(C.POINTER(C.c_float)), float(scale), xbase.numel(),
+                    mbase.numel() if has_mask else 0, _lib.current_stream()))
                 if stage == 0 and has_mask:
                     pred_mask = P0
         return xbase, (P0 if has_mask else None), (mbase if has_mask else None)

@@ -8,8 +8,9 @@ forward itself is executed by libpdm.so (hand-written sm_100a kernels behind the
 their own ``forward`` is never used and there is no PyTorch/CPU fallback.
 
 Documented deviations: ``patch_factor`` is accepted and ignored so the shipped config
-files load; ``use_ground_truth=True``, ``mlp_time_embed=True``, ``qkv_bias=True`` and
-``use_checkpoint=True`` (training-only) are rejected.
+files load; ``mlp_time_embed=True``, ``qkv_bias=True``, ``qk_scale``, ``conv=False`` and ``skip=False`` are rejected (no
+MSCOCO t2i config uses them).  ``forward(..., use_ground_truth=True)`` (``libs/uvit_t2i.py:380, 486-496``) IS
+implemented (``pdm_nnet_forward_ex`` with ``PDM_FWD_GROUND_TRUTH``).
 """
 from __future__ import annotations
 
@@ -173,6 +174,14 @@ class UViT(nn.Module):
 
     def __del__(self):
         self._release()
+
+    # The engine handle is a per-object device resource: copies (copy.copy / copy.deepcopy, pickle, torch.save of the
+    # whole module, e.g. an EMA twin of the network) must not alias it (double pdm_destroy) nor try to pickle
+    # a ctypes pointer.  A copy lazily creates its own engine on first use.
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state["_handle"] = state["_handle_device"] = state["_fingerprint"] = None
+        return state
 
     def engine(self) -> C.c_void_p:
         """Create the device engine (once per device) and upload parameters whenever they changed."""

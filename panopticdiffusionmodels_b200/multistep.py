@@ -37,6 +37,7 @@ def multistep_record(ns, t_hist, t, n_time: float = 1000.0) -> List[float]:
     rec[1], rec[2] = float(ns.marginal_alpha(p0)), float(ns.marginal_std(p0))
     rec[3] = float(sig_t / sig0)
     rec[11] = float(o)
+    rec[15] = 1.0  # record kind: multistep (include/pdm.h)
     if o == 1:
         phi_1 = (torch.exp(-h) - 1.0) / (-1.0)
         rec[4] = float(a_t * phi_1)
@@ -79,6 +80,10 @@ def sample_multistep(solver, x, steps, eps, T, order, skip_type, mask_token):
     if not x.is_cuda:
         raise RuntimeError("DPM_Solver (libpdm) has no CPU path: x must be a CUDA tensor")
     plan = build_multistep_plan(solver.noise_schedule, steps, order, eps, T, skip_type, solver.n_time)
+    if getattr(solver.model, "_pdm_fast_path", False):
+        # our UViT + guidance: the whole 2M / 3M loop runs on the device (pdm_sample: one forward + ONE fused update kernel
+        # per step, history ring in the engine workspace, captured into a CUDA graph)
+        return solver.model.run_plan(x, mask_token, plan, use_graph=solver.use_graph)
     L = _lib.lib()
     dev = x.device
     f32 = dict(device=dev, dtype=torch.float32)
@@ -92,25 +97,15 @@ def sample_multistep(solver, x, steps, eps, T, order, skip_type, mask_token):
         phist = [torch.empty_like(m_cur) for _ in range(3)]
     B = x.shape[0]
     model = solver.model
-    fused_cfg = getattr(model, "_pdm_fast_path", False) and model.empty_context is not None
+    pair = getattr(model, "eval_pair", None)
     with torch.cuda.device(dev):
         for k, rec in enumerate(plan):
             t_model = float(rec[0])
             X0, X1, X2 = hist[k % 3], hist[(k - 1) % 3], hist[(k - 2) % 3]
-            if fused_cfg:
-                # one 2B-row forward; the guidance combine happens inside the update kernel
-                ctx2 = torch.cat([model.context, model.empty_context.unsqueeze(0).expand(B, -1, -1)], 0).to(**f32)
-                tt = torch.full((2 * B,), t_model, **f32)
-                x2 = torch.cat([cur, cur], 0)
-                if has_mask:
-                    noise, y = model.nnet(x2, tt, ctx2, mask_token=torch.cat([m_cur, m_cur], 0))
-                    pc, pu = y[:B].contiguous(), y[B:].contiguous()
-                else:
-                    noise = model.nnet(x2, tt, ctx2)
-                    pc = pu = None
-                ec, eu, scale = noise[:B].contiguous(), noise[B:].contiguous(), model.scale
+            t_cont = torch.full((B,), t_model / solver.n_time, **f32)
+            if pair is not None:
+                ec, eu, pc, pu, scale = pair(cur, t_cont, mask_token=m_cur if has_mask else None)
             else:
-                t_cont = torch.full((B,), t_model / solver.n_time, **f32)
                 out = model(cur, t_cont, panoptic=None, mask_token=m_cur if has_mask else None)
                 noise, pm = out if isinstance(out, tuple) else (out, None)
                 ec, eu, scale = noise.to(**f32).contiguous(), None, 0.0

@@ -57,6 +57,27 @@ class CFGModel:
         c, u, pc, pu = noise[:B], noise[B:], y[:B], y[B:]
         return c + self.scale * (c - u), pc + self.scale * (pc - pu)
 
+    # ---- un-combined evaluation for the solver's own callback loop: the combine stays in the fused update kernel ----
+    @torch.no_grad()
+    def eval_pair(self, x, t_continuous, mask_token=None, use_ground_truth=False):
+        """-> (eps_c, eps_u, pm_c, pm_u, scale): cond / uncond halves of ONE 2B-row forward (eps_u / pm_u None without
+        guidance); contiguous views, no arithmetic."""
+        t = t_continuous * self.n_time
+        B = x.shape[0]
+        gt = bool(use_ground_truth)
+        if self.empty_context is None:
+            out = self.nnet(x, t, self.context, mask_token=mask_token, use_ground_truth=gt)
+            noise, y = out if mask_token is not None else (out, None)
+            return noise, None, y, None, 0.0
+        ctx2 = torch.cat([self.context, self.empty_context.unsqueeze(0).expand(B, -1, -1)], dim=0)
+        x2 = torch.cat([x, x], dim=0)
+        t2 = torch.cat([t, t], dim=0) if torch.is_tensor(t) and t.dim() > 0 else t
+        if mask_token is None:
+            noise = self.nnet(x2, t2, ctx2)
+            return noise[:B], noise[B:], None, None, self.scale
+        noise, y = self.nnet(x2, t2, ctx2, mask_token=torch.cat([mask_token, mask_token], dim=0), use_ground_truth=gt)
+        return noise[:B], noise[B:], y[:B], y[B:], self.scale
+
     # ---- fast path: whole loop on the device ----
     @torch.no_grad()
     def run_plan(self, x, mask_token, plan: np.ndarray, use_graph: bool = True) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
@@ -84,11 +105,12 @@ class JointSampler:
     """``dpm_solver_sample`` of the live path: noise init, mask init, DPM-Solver-fast order 3, CFG."""
 
     def __init__(self, nnet, z_shape=(4, 32, 32), mask_channels: int = 8, scale: float = 1.0, cfg: bool = True,
-                 sample_steps: int = 50, betas=None):
+                 sample_steps: int = 50, betas=None, method: str = "fast"):
         self.nnet = nnet
         self.z_shape = tuple(z_shape)
         self.mask_channels = mask_channels
         self.scale, self.cfg, self.sample_steps = scale, cfg, sample_steps
+        self.method = method  # 'fast' (singlestep 3,...,3,2: the live path, train_t2i_discrete.py:516) | 'multistep' (3M)
         betas = stable_diffusion_beta_schedule() if betas is None else betas
         self.N = len(betas)
         self.noise_schedule = NoiseScheduleVP(schedule="discrete", betas=torch.tensor(betas).float())
@@ -109,6 +131,6 @@ class JointSampler:
         steps = self.sample_steps if steps is None else steps
         if use_panoptic:
             return solver.sample(z_init, steps=steps, eps=1.0 / self.N, T=1.0, order=3, mask_token=mask_init,
-                                 enable_mask_opt=True, enable_panoptic=True)
-        z, _ = solver.sample(z_init, steps=steps, eps=1.0 / self.N, T=1.0, order=3)
+                                 enable_mask_opt=True, enable_panoptic=True, method=self.method)
+        z, _ = solver.sample(z_init, steps=steps, eps=1.0 / self.N, T=1.0, order=3, method=self.method)
         return z, None

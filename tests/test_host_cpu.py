@@ -86,3 +86,46 @@ def test_rejected_options():
         UViT(**dict(TINY, mlp_time_embed=True))
     with pytest.raises(TypeError):
         UViT(**dict(TINY, bogus_kwarg=1))
+
+
+def test_config_table_matches_reference_files():
+    """configs.get_config == the reference's configs/mscoco_uvit_*.py key by key (fixture: the flattened tables of the four
+    reference files, written by executing them through the ml_collections shim), except the machine-specific paths."""
+    import json
+    from panopticdiffusionmodels_b200 import configs
+
+    def flat(c, pre=""):
+        out = {}
+        for k, v in c.items():
+            if hasattr(v, "items"):
+                out.update(flat(v, pre + k + "."))
+            else:
+                out[pre + k] = list(v) if isinstance(v, tuple) else v
+        return out
+
+    ref = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_configs.json")))
+    local_paths = {"dataset.path", "sample.path", "pretrained"}
+    for name in configs.NAMES:
+        ours, want = flat(configs.get_config(name)), ref[name]
+        assert set(ours) == set(want), name
+        for k in want:
+            if k not in local_paths:
+                assert ours[k] == want[k], (name, k, ours[k], want[k])
+
+
+def test_module_copies_do_not_share_the_engine_handle():
+    """copy.deepcopy(nnet) (e.g. an EMA twin), pickling and torch.save of the
+    whole module must work after an engine exists, and a copy must never alias the C handle (double pdm_destroy)."""
+    import copy
+    import ctypes as C
+    import pickle
+    from panopticdiffusionmodels_b200.libs.uvit_t2i import UViT
+    net = UViT(separate=False, **TINY)
+    net._handle = C.c_void_p(0x1234)          # stand-in for a live engine (no GPU here)
+    net._handle_device, net._fingerprint = "cuda:0", ("x",)
+    try:
+        for dup in (copy.deepcopy(net), copy.copy(net), pickle.loads(pickle.dumps(net))):
+            assert dup._handle is None and dup._handle_device is None and dup._fingerprint is None
+            assert set(dup.state_dict()) == set(net.state_dict())
+    finally:
+        net._handle = None                    # do not hand the fake pointer to pdm_destroy

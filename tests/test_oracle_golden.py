@@ -107,3 +107,30 @@ def test_bits_roundtrip():
     assert bits.shape == (1, 8, 16, 16)
     assert int(bits[0, 0, 15, 15]) == 1 and int(bits[0, 7, 0, 1]) == 1  # MSB first
     assert torch.equal(dpm_oracle.bits2int((bits * 2.0 - 1.0) > 0).long(), ids)
+
+
+def test_codec_matches_reference():
+    """oracle int2bits / bits2int against the outputs of the reference's utils.int2bits / utils.bits2int (utils.py:475-518;
+    tests/golden/make_round2.py codec): all 256 ids, random bit patterns, sign-thresholded analog bits incl. exact zeros."""
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "codec.npz"))
+    ids = torch.from_numpy(z["ids"])
+    assert torch.equal(dpm_oracle.int2bits(ids).to(torch.int32), torch.from_numpy(z["bits"]).to(torch.int32))
+    assert torch.equal(dpm_oracle.bits2int(torch.from_numpy(z["pattern"])), torch.from_numpy(z["labels"]))
+    assert torch.equal(dpm_oracle.bits2int(torch.from_numpy(z["analog"]) > 0), torch.from_numpy(z["labels_analog"]))
+
+
+@pytest.mark.parametrize("tag", ["mid", "large", "small_512"])
+def test_full_depth_forward_matches_reference(tag):
+    """BASELINE configs 3 / 4 / 5 at full depth and real geometry (batch 1): the oracle against the REAL reference forward
+    (tests/golden/make_round2.py forwards).  A few seconds of CPU each."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_round2 import build_model, fwd_inputs
+    ref = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "configs_fwd.npz"))
+    net, kw = build_model(tag)
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    x, m, ctx, t = fwd_inputs(kw)
+    torch.set_num_threads(os.cpu_count())
+    noise, y = uvit_oracle.uvit_forward(sd, kw, x, t, ctx, m)
+    rn, ry = torch.from_numpy(ref[f"{tag}/noise"]), torch.from_numpy(ref[f"{tag}/y"])
+    assert (noise - rn).abs().max() <= 2e-5 * rn.abs().max(), float((noise - rn).abs().max() / rn.abs().max())
+    assert (y - ry).abs().max() <= 2e-5 * max(1.0, float(ry.abs().max()))

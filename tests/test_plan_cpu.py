@@ -124,3 +124,48 @@ def test_multistep_plan_matches_reference_updates():
     assert torch.equal(out2, g["m2"])
     plan = build_multistep_plan(ns, 10, 3, eps=1e-3, T=1.0, skip_type="time_uniform")
     assert plan.shape == (10, P.PLAN_STRIDE) and list(plan[:4, 11]) == [1, 2, 3, 3] and plan[0, 0] == 1000.0
+
+
+@pytest.mark.parametrize("method,order,steps", [("fast", 3, 50), ("fast", 3, 20), ("fast", 3, 7), ("fast", 3, 9), ("fast", 2, 11),
+                                                ("singlestep", 3, 9), ("singlestep", 2, 8), ("singlestep", 1, 4),
+                                                ("multistep", 3, 20), ("multistep", 2, 10), ("multistep", 1, 5)])
+@pytest.mark.parametrize("mask_opt", [True, False])
+@pytest.mark.parametrize("skip_type", ["time_uniform", "logSNR", "t2"])
+def test_c_planner_matches_host_planner(method, order, steps, mask_opt, skip_type):
+    """pdm_solver_plan (C ABI host planner, csrc/plan.cu) against the Python host planner, whose float32 torch ops are what the
+    reference evaluates.  Structure (stages, flags, orders, record kinds) is identical; every coefficient agrees to <= 4e-6
+    relative (+ 2e-7 absolute; 3e-4 for the two ill-conditioned 3M coefficients): the residue is libm-vs-SLEEF rounding of exp / log / log1p / expm1 and torch.linspace's
+    per-SIMD-chunk rounding, amplified where a coefficient is a difference of nearby numbers."""
+    from panopticdiffusionmodels_b200 import dpm_solver_pp as P
+    from panopticdiffusionmodels_b200.multistep import build_multistep_plan
+    from panopticdiffusionmodels_b200.sampling import stable_diffusion_beta_schedule
+    betas = torch.tensor(stable_diffusion_beta_schedule()).float()
+    ns = P.NoiseScheduleVP("discrete", betas=betas)
+    if method == "multistep":
+        if not mask_opt:
+            pytest.skip("multistep has no pass-through variant")
+        want = build_multistep_plan(ns, steps, order, 1e-3, 1.0, skip_type)
+    else:
+        want = P.build_plan(ns, steps, order, 1e-3, 1.0, skip_type, method, mask_opt=mask_opt)
+    got = P.build_plan_c(betas, steps, order, 1e-3, 1.0, skip_type, method, mask_opt=mask_opt)
+    assert got.shape == want.shape and got.dtype == np.float32
+    flags = [8, 9, 10, 11, 12, 15] if method != "multistep" else [11, 15]
+    assert np.array_equal(got[:, flags], want[:, flags])
+    assert np.array_equal(got[:, 13:15], want[:, 13:15])
+    err = np.abs(got.astype(np.float64) - want.astype(np.float64))
+    tol = 4e-6 * np.abs(want.astype(np.float64)) + 2e-7
+    if method == "multistep":
+        # the 3M coefficients (e^-h - 1) / h + 1 and (e^-h - 1 + h) / h^2 - 1/2 cancel to O(h): a float32 ulp of e^-h is
+        # amplified by 1 / h .. 1 / h^2 -- in the reference's own arithmetic as much as here
+        tol[:, 5:7] = 3e-4 * np.abs(want[:, 5:7].astype(np.float64)) + 2e-7
+    assert (err <= tol).all(), (float((err / (np.abs(want) + 1e-30)).max()), np.argwhere(err > tol)[:5])
+
+
+def test_c_planner_errors():
+    from panopticdiffusionmodels_b200 import dpm_solver_pp as P
+    from panopticdiffusionmodels_b200.sampling import stable_diffusion_beta_schedule
+    betas = torch.tensor(stable_diffusion_beta_schedule()).float()
+    with pytest.raises(RuntimeError, match="order"):
+        P.build_plan_c(betas, 10, 4, method="singlestep")
+    with pytest.raises(RuntimeError, match="steps >= order"):
+        P.build_plan_c(betas, 2, 3, method="multistep")
