@@ -172,6 +172,31 @@ int pdm_bits2int(const float* pred_mask, int32_t* labels, int32_t B, int32_t nbi
  * ids [B,H,W] int32 -> analog bits [B,8,H,W] float32 in {-1,+1}. */
 int pdm_int2bits(const int32_t* ids, float* bits, int32_t B, int32_t nbits, int32_t hw, void* stream);
 
+/* ---- VAE decoder (the step after the loop: latents -> images) ---------------------------------------------------------
+ * replaces: libs/autoencoder.py:303-410 (Decoder) + :446-450 (FrozenAutoencoderKL.decode), called per mini-batch by
+ * eval_t2i_discrete.py:74-84 (decode_large_batch) / utils.py:627-637.  Mirrors `ddconfig` of libs/autoencoder.py:471-485. */
+typedef struct pdm_vae* pdm_vae_handle;
+typedef struct pdm_vae_config {
+    int32_t ch;             /* 128 */
+    int32_t num_levels;     /* len(ch_mult) = 4 */
+    int32_t ch_mult[8];     /* 1, 2, 4, 4 */
+    int32_t num_res_blocks; /* 2 */
+    int32_t z_channels;     /* 4 */
+    int32_t embed_dim;      /* 4 */
+    int32_t out_ch;         /* 3 */
+    float scale_factor;     /* 0.18215 (configs: 0.23010) */
+} pdm_vae_config;
+int pdm_vae_create(const pdm_vae_config* cfg, pdm_vae_handle* out);
+int pdm_vae_destroy(pdm_vae_handle h);
+/* `key` = key of the reference autoencoder state_dict (`decoder.*`, `post_quant_conv.*`); `encoder.*` / `quant_conv.*` /
+ * `loss.*` are accepted and ignored (the sampling path only decodes).  dev_f32: device float32 tensor of the given shape. */
+int pdm_vae_set_param(pdm_vae_handle h, const char* key, const void* dev_f32, const int64_t* shape, int32_t ndim, void* stream);
+int pdm_vae_finalize_params(pdm_vae_handle h, void* stream);
+/* z [n, 4, s, s] float32 (scaled latents, as the sampler returns them) -> out [n, out_ch, 8 s, 8 s] float32 in [-1, 1]-ish
+ * (the caller applies unpreprocess: 0.5 (x + 1) clamp, train_t2i_discrete.py:584).  latent_size s in {16, 32, 64, ...}. */
+int pdm_vae_decode(pdm_vae_handle h, const float* z, float* out, int32_t n, int32_t latent_size, void* stream);
+int pdm_vae_workspace_bytes(pdm_vae_handle h, int32_t n, int32_t latent_size, size_t* bytes);
+
 /* diagnostics */
 const char* pdm_last_error(void);
 int pdm_abi_version(void);

@@ -27,6 +27,11 @@ class PdmConfig(C.Structure):
         "num_clip_token", "num_panoptic_class", "enable_panoptic", "separate")]
 
 
+class PdmVaeConfig(C.Structure):
+    _fields_ = [("ch", C.c_int32), ("num_levels", C.c_int32), ("ch_mult", C.c_int32 * 8), ("num_res_blocks", C.c_int32),
+                ("z_channels", C.c_int32), ("embed_dim", C.c_int32), ("out_ch", C.c_int32), ("scale_factor", C.c_float)]
+
+
 # symbol -> (restype, argtypes); mirrors include/pdm.h one to one
 _P = C.c_void_p
 SIGNATURES = {
@@ -53,6 +58,12 @@ SIGNATURES = {
     "pdm_debug_layernorm": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                                       C.POINTER(C.c_float), _P]),
     "pdm_debug_ln_chain": (C.c_int, [_P] * 10 + [C.c_int32] * 6 + [C.POINTER(C.c_float), _P]),
+    "pdm_vae_create": (C.c_int, [C.POINTER(PdmVaeConfig), C.POINTER(_P)]),
+    "pdm_vae_destroy": (C.c_int, [_P]),
+    "pdm_vae_set_param": (C.c_int, [_P, C.c_char_p, _P, C.POINTER(C.c_int64), C.c_int32, _P]),
+    "pdm_vae_finalize_params": (C.c_int, [_P, _P]),
+    "pdm_vae_decode": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, _P]),
+    "pdm_vae_workspace_bytes": (C.c_int, [_P, C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]),
     "pdm_last_error": (C.c_char_p, []),
     "pdm_abi_version": (C.c_int, []),
     "pdm_launch_count": (C.c_int64, []),

@@ -19,7 +19,7 @@ CSRC = os.path.join(HERE, "csrc")
 TAG = os.environ.get("PDM_BUILD_TAG", "")  # development: a second library (e.g. a -DPDM_ATTN_TRACE build) next to the product one
 OBJ = os.path.join(HERE, "build" + TAG)
 LIB = os.path.join(HERE, f"libpdm{TAG}.so")
-SOURCES = ["elementwise.cu", "gemm_simt.cu", "gemm_tc.cu", "attention_simt.cu", "attention_tc3.cu", "plan.cu", "engine.cu"]
+SOURCES = ["elementwise.cu", "gemm_simt.cu", "gemm_tc.cu", "attention_simt.cu", "attention_tc3.cu", "plan.cu", "vae.cu", "engine.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",

@@ -149,3 +149,11 @@ def save_mask_png(labels: torch.Tensor, path: str, colormap: Optional[torch.Tens
         labels = labels.unsqueeze(0)
     rgb = color_map(labels, colormap)[0].permute(1, 2, 0).to("cpu", torch.uint8).numpy()
     Image.fromarray(rgb).save(path)
+
+
+def save_image_png(img: torch.Tensor, path: str) -> None:
+    """One image ``(3, H, W)`` in [0, 1] -> PNG, the rounding of ``torchvision.utils.save_image`` (``utils.py:634``):
+    ``img * 255 + 0.5`` clamped to [0, 255], truncated to uint8."""
+    from PIL import Image
+    arr = img.detach().float().mul(255).add_(0.5).clamp_(0, 255).permute(1, 2, 0).to("cpu", torch.uint8).numpy()
+    Image.fromarray(arr).save(path)

@@ -30,6 +30,7 @@ struct Error : public std::runtime_error {
         if (!(cond)) throw ::pdm::Error(std::string("pdm: ") + (msg));          \
     } while (0)
 
+void set_last_error(const std::string& msg);  // thread-local message behind pdm_last_error() (engine.cu)
 extern std::atomic<long long> g_launch_count;
 inline void count_launch() { g_launch_count.fetch_add(1, std::memory_order_relaxed); }
 inline void check_launch(const char* what) {
@@ -114,6 +115,11 @@ struct GemmProblem {
     // (gamma * W, centred along K) and `bias` holds bias + W.beta, so that out = rstd * acc + bias == LN(x).W^T + b
     const float* ln_rstd = nullptr;  // [rows] 1 / sqrt(var + eps) of x, from ln_rstd() over the producer's row sums
     int ln_rstd_bs = 0;
+    // ---- implicit-GEMM 3x3 convolution, stride 1, zero padding 1 (tcgen05 kernel only; VAE decoder, vae.cu) ----
+    // conv_H > 0: A1 is an NHWC activation [conv_N, conv_H, conv_W, conv_C] (bf16), rows = output pixels in (n, h, w) order
+    // (Lr = conv_N * conv_H * conv_W, nb = 1), K1 = 9 * conv_C with k = (ky * 3 + kx) * conv_C + c, W16 = [N, 9 * conv_C].
+    // The A tile of tap (ky, kx) is ONE shifted TMA box of the activation; the border comes from the out-of-bounds zero fill.
+    int conv_N = 0, conv_H = 0, conv_W = 0, conv_C = 0;
 };
 
 void gemm_simt_f32(const GemmProblem& p, cudaStream_t s);

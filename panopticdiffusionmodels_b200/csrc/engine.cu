@@ -109,6 +109,10 @@ struct ProfEvent {
 
 }  // namespace pdm
 
+namespace pdm {
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+}  // namespace pdm
+
 using namespace pdm;
 
 struct pdm_engine {

@@ -33,6 +33,8 @@ CUtensorMap make_tmap_bf16_3d(const void* ptr, long long K, long long rows, long
                               int box_rows, int box_k);
 CUtensorMap make_tmap_3d(const void* ptr, int esize, long long K, long long rows, long long nbatch, long long bs,
                          int box_rows, int box_k, CUtensorMapSwizzle swz);
+CUtensorMap make_tmap_bf16_nhwc(const void* ptr, long long C, long long W, long long H, long long N, int box_w, int box_h,
+                                int box_c);
 
 namespace {
 
@@ -105,6 +107,9 @@ struct TcParams {
     // deferred LayerNorm, consumer side (bf16 form): out = rstd[row] * acc + bias[n]  (weight centred along K: no mean term)
     const float* ln_rstd;
     long long ln_bs;
+    // implicit-GEMM 3x3 convolution (conv_hw > 0): A through a 4-D map [C, W, H, N]
+    int conv_hw, conv_W, conv_H, conv_kbc;  // pixels per image, width, height, k-blocks per tap (C / 64)
+    int conv_ht, conv_wt;                   // tile = conv_ht rows x conv_wt pixels (128 consecutive output pixels)
 };
 
 // GELU(erf) for the bf16 path (libs/timm.py:101 -> nn.GELU()).  x.Phi(x) = 0.5 x (1 + tanh(x (a + b x^2 + c x^4)))
@@ -293,13 +298,38 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
                     t0 = (mt - b * p.tpb) * BM;
                 }
                 const int n0 = nt * BN + (int)rank * (BN / NCTA);
+                // convolution: the tile's 128 output pixels = conv_ht image rows x conv_wt pixels starting at (cn, ch0, cw0)
+                int cn = 0, ch0 = 0, cw0 = 0;
+                if (p.conv_hw) {
+                    cn = p.n_mtiles;  // padding tile: an image index past the end -> zero fill
+                    if (mt < p.n_mtiles) {
+                        const int pix = mt * BM;
+                        cn = pix / p.conv_hw;
+                        const int rem = pix - cn * p.conv_hw;
+                        ch0 = rem / p.conv_W;
+                        cw0 = rem - ch0 * p.conv_W;
+                    }
+                }
                 for (int kb = 0; kb < p.KB; ++kb) {
                     ptx::mbar_wait(&empty[stage], phase ^ 1);
                     const uint32_t sa = smem_u + stage * STAGE_BYTES;
                     const uint32_t sb = sa + A_BYTES;
                     const CUtensorMap* ta = kb < p.KB1 ? &tmA1 : &tmA2;
                     const int ka = (kb < p.KB1 ? kb : kb - p.KB1) * BK;
-                    if (ptx::elect_one()) {
+                    if (p.conv_hw) {
+                        const int tap = kb / p.conv_kbc, cb = kb - tap * p.conv_kbc;
+                        const int ky = tap / 3, kx = tap - 3 * ky;
+                        if (ptx::elect_one()) {
+                            if (rank == 0) ptx::mbar_expect_tx(&full[stage], NCTA * STAGE_BYTES);
+                            if (NCTA == 2) {
+                                ptx::tma_load_4d_2sm(&tmA1, &full[stage], sa, cb * BK, cw0 + kx - 1, ch0 + ky - 1, cn);
+                                ptx::tma_load_3d_2sm(&tmB, &full[stage], sb, kb * BK, n0, 0);
+                            } else {
+                                ptx::tma_load_4d(&tmA1, &full[stage], sa, cb * BK, cw0 + kx - 1, ch0 + ky - 1, cn);
+                                ptx::tma_load_3d(&tmB, &full[stage], sb, kb * BK, n0, 0);
+                            }
+                        }
+                    } else if (ptx::elect_one()) {
                         if (rank == 0) ptx::mbar_expect_tx(&full[stage], NCTA * STAGE_BYTES);
                         if (NCTA == 2) {
                             ptx::tma_load_3d_2sm(ta, &full[stage], sa, ka, t0, b);
@@ -813,7 +843,18 @@ void launch(const GemmProblem& g, cudaStream_t s) {
     p.npart = ceil_div(g.N, LN_PART);
     p.ln_rstd = g.ln_rstd;
     p.ln_bs = g.ln_rstd_bs ? g.ln_rstd_bs : g.Lr;
-    const CUtensorMap tmA1 = make_tmap_bf16_3d(g.A1, g.K1, g.Lr, g.nb, g.a1_bs ? g.a1_bs : g.Lr, BM, BK);
+    p.conv_hw = p.conv_W = p.conv_H = p.conv_kbc = p.conv_ht = p.conv_wt = 0;
+    if (g.conv_H > 0) {
+        p.conv_hw = g.conv_H * g.conv_W;
+        p.conv_W = g.conv_W;
+        p.conv_H = g.conv_H;
+        p.conv_kbc = g.conv_C / BK;
+        p.conv_wt = std::min(g.conv_W, BM);
+        p.conv_ht = BM / p.conv_wt;
+    }
+    const CUtensorMap tmA1 = g.conv_H > 0
+                                 ? make_tmap_bf16_nhwc(g.A1, g.conv_C, g.conv_W, g.conv_H, g.conv_N, p.conv_wt, p.conv_ht, BK)
+                                 : make_tmap_bf16_3d(g.A1, g.K1, g.Lr, g.nb, g.a1_bs ? g.a1_bs : g.Lr, BM, BK);
     const CUtensorMap tmA2 =
         g.A2 ? make_tmap_bf16_3d(g.A2, g.K2, g.Lr, g.nb, g.a2_bs ? g.a2_bs : g.Lr, BM, BK) : tmA1;
     const CUtensorMap tmB = make_tmap_bf16_3d(g.W16, K, g.N, 1, g.N, BN / NCTA, BK);
@@ -856,6 +897,32 @@ CUtensorMap make_tmap_3d(const void* ptr, int esize, long long K, long long rows
                               const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     PDM_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (code " + std::to_string((int)r) + ")");
+    std::lock_guard<std::mutex> lk(g_map_mutex);
+    g_map_cache[key] = m;
+    return m;
+}
+
+// bf16 NHWC activation [N, H, W, C] as a 4-D map [C, W, H, N]; box = [box_c, box_w, box_h, 1]; SWIZZLE_128B.  The box rows
+// land in shared memory in (h, w) order: box_h * box_w = 128 rows of 128 bytes = one K-major UMMA operand tile.
+CUtensorMap make_tmap_bf16_nhwc(const void* ptr, long long C, long long W, long long H, long long N, int box_w, int box_h,
+                                int box_c) {
+    MapKey key(ptr, -C, W * 65536 + H, N, -1, box_w * 256 + box_h, box_c);
+    {
+        std::lock_guard<std::mutex> lk(g_map_mutex);
+        auto it = g_map_cache.find(key);
+        if (it != g_map_cache.end()) return it->second;
+    }
+    PDM_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "tensor map: base must be 16-byte aligned");
+    PDM_REQUIRE((C * 2) % 16 == 0, "tensor map: channel pitch must be a multiple of 16 bytes");
+    CUtensorMap m;
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)(C * 2), (cuuint64_t)(W * C * 2), (cuuint64_t)(H * W * C * 2)};
+    cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    PDM_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (4-D) failed (code " + std::to_string((int)r) + ")");
     std::lock_guard<std::mutex> lk(g_map_mutex);
     g_map_cache[key] = m;
     return m;
@@ -905,6 +972,13 @@ void gemm_tc_bf16(const GemmProblem& g, cudaStream_t s) {
     PDM_REQUIRE(g.out32 || g.N % 8 == 0, "gemm_tc: the bf16-only output form needs N % 8 == 0");
     PDM_REQUIRE((!g.stats && !g.statsb && !g.out2b) || g.out32, "gemm_tc: row sums / out2b belong to the fp32-output form");
     PDM_REQUIRE(!g.statsb || g.stats, "gemm_tc: statsb needs stats");
+    if (g.conv_H > 0) {
+        const int hw = g.conv_H * g.conv_W;
+        PDM_REQUIRE(g.nb == 1 && !g.A2 && g.conv_C % BK == 0 && g.K1 == 9 * g.conv_C && g.Lr == g.conv_N * hw,
+                    "gemm_tc(conv): K1 = 9 C with C % 64 == 0, rows = N H W");
+        PDM_REQUIRE(hw % BM == 0 && (g.conv_W >= BM ? g.conv_W % BM == 0 : (BM % g.conv_W == 0 && g.conv_H % (BM / g.conv_W) == 0)),
+                    "gemm_tc(conv): a 128-pixel tile must be whole image rows (or a row segment) of one image");
+    }
     static const bool one_cta = getenv("PDM_GEMM_1CTA") != nullptr;
     // TMA-store epilogue: the HBM-bound read-modify-write GEMMs (proj, zero-conv: K <= 1024).  It leaves room for a 3-stage
     // operand ring only, so the tensor-bound K >= 2048 forms (fc2) and the skip GEMM keep the register-transpose epilogue.

@@ -245,6 +245,21 @@ __device__ __forceinline__ void tma_load_3d_2sm(const CUtensorMap* m, uint64_t* 
         "r"(smem_u32(bar) & 0xFEFFFFFFu)
         : "memory");
 }
+// 4-D forms (implicit-GEMM convolution: [C, W, H, N] activation, box [64, Wt, Ht, 1], out-of-bounds = zero padding)
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* m, uint64_t* bar, uint32_t dst, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_2sm(const CUtensorMap* m, uint64_t* bar, uint32_t dst, int c0, int c1, int c2,
+                                                int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(c2), "r"(c3),
+        "r"(smem_u32(bar) & 0xFEFFFFFFu)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_alloc_2sm(uint32_t* dst_smem, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
                  "r"(ncols)

@@ -1,0 +1,722 @@
+// VAE decoder of the latent-diffusion autoencoder (libs/autoencoder.py:303-410 Decoder, :446-450 FrozenAutoencoderKL.decode)
+// on sm_100a: the step after the sampling loop (eval_t2i_discrete.py:74-84 decode_large_batch, utils.py:627-637).
+//
+//   z / scale_factor -> post_quant_conv (1x1) -> conv_in (3x3) -> mid { ResnetBlock, AttnBlock, ResnetBlock }
+//   -> up levels { (num_res_blocks + 1) x ResnetBlock, nearest 2x Upsample + 3x3 conv } -> GroupNorm, swish, conv_out (3x3)
+//
+// Layout: activations are NHWC -- the residual stream in fp32, every convolution operand in bf16.  The 3x3 convolutions
+// (all but the 4-channel conv_in and the 3-channel conv_out: > 99 % of the FLOPs) run on the tcgen05 GEMM kernel of
+// gemm_tc.cu as IMPLICIT GEMMs: 128 consecutive output pixels are one accumulator tile, K = 9 taps x C_in, and the A tile of
+// tap (ky, kx) is one TMA box of the activation shifted by (ky - 1, kx - 1) whose out-of-bounds part is zero-filled by the
+// TMA unit (= the padding); nothing is ever unfolded in memory.  Bias, the residual add (x += conv2(...)) and the fp32 store
+// are the GEMM epilogue.  1x1 convolutions (nin_shortcut, q / k / v / proj_out) are plain GEMMs on the flat [pixels, C] view.
+// GroupNorm (32 groups, eps 1e-6) is a statistics pass (fp32 partial sums in a fixed order, fp64 combine) + one fused
+// normalise * gamma + beta -> swish -> bf16 pass that writes the next convolution's operand; the nearest-neighbour upsample
+// is fused into the operand write of the Upsample convolution.  The single-head 512-channel attention of the mid block
+// (1024 tokens at 256 px) is per image S = q k^T (GEMM) -> row softmax -> O = P V (GEMM against V^T, which a GEMM with the
+// roles of weight and activation swapped produces directly; v's bias commutes with the softmax and is folded into
+// proj_out's).
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/pdm.h"
+#include "common.cuh"
+
+namespace pdm {
+namespace {
+
+constexpr int GN_GROUPS = 32;
+constexpr int GN_PPB = 256;  // pixels per GroupNorm-statistics block
+
+// ---------------------------------------------------------------------------------------------- GroupNorm
+// partial (sum, sum of squares) per (image, pixel slab, group): block = 256 threads over a slab of pixels, float4 channel
+// vectors.  Every reduction runs in a FIXED order (no floating-point atomics): the decode is bit-reproducible and a sample
+// does not depend on which other samples share its batch.
+__global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__ x, float* __restrict__ part, int hw, int C,
+                                                       int pix_per_block) {
+    __shared__ float ts[256][2];
+    const int n = blockIdx.y;
+    const int c4n = C >> 2;                 // float4 columns
+    const int cpg4 = (C / GN_GROUPS) >> 2;  // float4 columns per group (>= 1)
+    const int col = threadIdx.x % c4n, prow = threadIdx.x / c4n, pstep = blockDim.x / c4n;
+    const int p0 = blockIdx.x * pix_per_block;
+    const int p1 = min(hw, p0 + pix_per_block);
+    float s1 = 0.f, s2 = 0.f;
+    if (prow < pstep) {
+        const float4* base = reinterpret_cast<const float4*>(x + ((long long)n * hw) * C) + col;
+        for (int p = p0 + prow; p < p1; p += pstep) {
+            const float4 v = __ldg(base + (long long)p * c4n);
+            s1 += (v.x + v.y) + (v.z + v.w);
+            s2 = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, s2))));
+        }
+    }
+    ts[threadIdx.x][0] = s1;
+    ts[threadIdx.x][1] = s2;
+    __syncthreads();
+    if (threadIdx.x < GN_GROUPS) {
+        const int g = threadIdx.x;
+        float a1 = 0.f, a2 = 0.f;
+        for (int r = 0; r < pstep; ++r)
+            for (int c = 0; c < cpg4; ++c) {
+                const int t = r * c4n + g * cpg4 + c;
+                a1 += ts[t][0];
+                a2 += ts[t][1];
+            }
+        float* o = part + (((long long)n * gridDim.x + blockIdx.x) * GN_GROUPS + g) * 2;
+        o[0] = a1;
+        o[1] = a2;
+    }
+}
+__global__ void gn_finalize_kernel(const float* __restrict__ part, float* __restrict__ mr, int n_images, int nblk, double count,
+                                   float eps) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_images * GN_GROUPS) return;
+    const int n = i / GN_GROUPS, g = i - n * GN_GROUPS;
+    double s1 = 0.0, s2 = 0.0;
+    for (int b = 0; b < nblk; ++b) {
+        const float* o = part + (((long long)n * nblk + b) * GN_GROUPS + g) * 2;
+        s1 += (double)o[0];
+        s2 += (double)o[1];
+    }
+    const double mean = s1 / count;
+    double var = s2 / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    mr[2 * i] = (float)mean;
+    mr[2 * i + 1] = (float)(1.0 / sqrt(var + (double)eps));
+}
+__device__ __forceinline__ float swish(float v) { return v / (1.f + __expf(-v)); }
+// y = GN(x) [* sigmoid(.)] -> bf16 NHWC (the next convolution's operand)
+__global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__ x, const float* __restrict__ mr,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       bf16* __restrict__ out, long long total4, int hw, int C, int act) {
+    const int c4n = C >> 2, cpg = C / GN_GROUPS;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < total4; i += stride) {
+        const int col = (int)(i % c4n);
+        const long long pix = i / c4n;
+        const int n = (int)(pix / hw);
+        const int g = (col * 4) / cpg;
+        const float mean = mr[((long long)n * GN_GROUPS + g) * 2], rstd = mr[((long long)n * GN_GROUPS + g) * 2 + 1];
+        const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+        const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma) + col), be = __ldg(reinterpret_cast<const float4*>(beta) + col);
+        float y0 = (v.x - mean) * rstd * ga.x + be.x, y1 = (v.y - mean) * rstd * ga.y + be.y;
+        float y2 = (v.z - mean) * rstd * ga.z + be.z, y3 = (v.w - mean) * rstd * ga.w + be.w;
+        if (act) { y0 = swish(y0); y1 = swish(y1); y2 = swish(y2); y3 = swish(y3); }
+        __nv_bfloat162 a = __floats2bfloat162_rn(y0, y1), b = __floats2bfloat162_rn(y2, y3);
+        reinterpret_cast<uint2*>(out)[i] = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+    }
+}
+// fp32 NHWC -> bf16 NHWC, optionally through a nearest-neighbour 2x upsample (F.interpolate(scale_factor=2, 'nearest'))
+__global__ void __launch_bounds__(256) convert_up_kernel(const float* __restrict__ x, bf16* __restrict__ out, long long total4,
+                                                         int H, int W, int C, int up) {
+    const int c4n = C >> 2;
+    const int Ho = up ? 2 * H : H, Wo = up ? 2 * W : W;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < total4; i += stride) {
+        const int col = (int)(i % c4n);
+        long long pix = i / c4n;
+        const int wo = (int)(pix % Wo);
+        pix /= Wo;
+        const int ho = (int)(pix % Ho);
+        const long long n = pix / Ho;
+        const int h = up ? ho >> 1 : ho, w = up ? wo >> 1 : wo;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(x) + ((n * H + h) * W + w) * c4n + col);
+        __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+        reinterpret_cast<uint2*>(out)[i] = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- the two narrow convolutions
+// z [n, Cz, h, w] (NCHW fp32) -> z / scale -> post_quant_conv (1x1) -> conv_in (3x3, pad 1) -> x [n, h, w, Cout] (NHWC fp32).
+// One thread per (pixel, 4 output channels); the 3x3 x Cz neighbourhood after the 1x1 is rebuilt per thread (Cz = 4).
+template <int CZ>
+__global__ void __launch_bounds__(128) conv_in_kernel(const float* __restrict__ z, const float* __restrict__ pq_w,
+                                                      const float* __restrict__ pq_b, const float* __restrict__ w,
+                                                      const float* __restrict__ b, float* __restrict__ out, int n, int H, int W,
+                                                      int Cout, float inv_scale) {
+    const int c4n = Cout >> 2;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)n * H * W * c4n) return;
+    const int col = (int)(i % c4n);
+    long long pix = i / c4n;
+    const int x0 = (int)(pix % W);
+    pix /= W;
+    const int y0 = (int)(pix % H);
+    const int img = (int)(pix / H);
+    float acc[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc[k] = __ldg(b + col * 4 + k);
+    for (int ky = 0; ky < 3; ++ky) {
+        const int yy = y0 + ky - 1;
+        if (yy < 0 || yy >= H) continue;
+        for (int kx = 0; kx < 3; ++kx) {
+            const int xx = x0 + kx - 1;
+            if (xx < 0 || xx >= W) continue;
+            float zin[CZ], pq[CZ];
+#pragma unroll
+            for (int c = 0; c < CZ; ++c) zin[c] = __ldg(z + (((long long)img * CZ + c) * H + yy) * W + xx) * inv_scale;
+#pragma unroll
+            for (int o = 0; o < CZ; ++o) {
+                float v = __ldg(pq_b + o);
+#pragma unroll
+                for (int c = 0; c < CZ; ++c) v = fmaf(__ldg(pq_w + o * CZ + c), zin[c], v);
+                pq[o] = v;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float* wr = w + (((long long)(col * 4 + k) * CZ) * 3 + ky) * 3 + kx;  // [Cout, CZ, 3, 3]
+#pragma unroll
+                for (int c = 0; c < CZ; ++c) acc[k] = fmaf(__ldg(wr + c * 9), pq[c], acc[k]);
+            }
+        }
+    }
+    reinterpret_cast<float4*>(out)[i] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+}
+// conv_out: bf16 NHWC [n, H, W, C] (already GroupNorm'ed + swish) -> 3x3 -> out [n, Co, H, W] (NCHW fp32), Co <= 4.
+// One thread per output pixel; weights staged in shared memory as [tap][c][Co].
+__global__ void __launch_bounds__(128) conv_out_kernel(const bf16* __restrict__ a, const float* __restrict__ w,
+                                                       const float* __restrict__ b, float* __restrict__ out, int n, int H, int W,
+                                                       int C, int Co) {
+    extern __shared__ float wsm[];  // [9][C][4]
+    for (int i = threadIdx.x; i < 9 * C * 4; i += blockDim.x) {
+        const int o = i & 3, c = (i >> 2) % C, tap = (i >> 2) / C;
+        wsm[i] = o < Co ? w[((long long)(o * C + c)) * 9 + tap] : 0.f;  // [Co, C, 3, 3]
+    }
+    __syncthreads();
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)n * H * W) return;
+    const int x0 = (int)(i % W), y0 = (int)((i / W) % H);
+    const long long img = i / ((long long)W * H);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int ky = 0; ky < 3; ++ky) {
+        const int yy = y0 + ky - 1;
+        if (yy < 0 || yy >= H) continue;
+        for (int kx = 0; kx < 3; ++kx) {
+            const int xx = x0 + kx - 1;
+            if (xx < 0 || xx >= W) continue;
+            const uint4* src = reinterpret_cast<const uint4*>(a + ((img * H + yy) * W + xx) * C);
+            const float4* wt = reinterpret_cast<const float4*>(wsm + (ky * 3 + kx) * C * 4);
+            for (int c8 = 0; c8 < C / 8; ++c8) {
+                const uint4 v = __ldg(src + c8);
+                const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float lo = __uint_as_float(u[q] << 16), hi = __uint_as_float(u[q] & 0xffff0000u);
+                    const float4 w0 = wt[c8 * 8 + 2 * q], w1 = wt[c8 * 8 + 2 * q + 1];
+                    acc[0] = fmaf(lo, w0.x, fmaf(hi, w1.x, acc[0]));
+                    acc[1] = fmaf(lo, w0.y, fmaf(hi, w1.y, acc[1]));
+                    acc[2] = fmaf(lo, w0.z, fmaf(hi, w1.z, acc[2]));
+                    acc[3] = fmaf(lo, w0.w, fmaf(hi, w1.w, acc[3]));
+                }
+            }
+        }
+    }
+    for (int o = 0; o < Co; ++o) out[((img * Co + o) * H + y0) * W + x0] = acc[o] + __ldg(b + o);
+}
+
+// ---------------------------------------------------------------------------------------------- attention helpers
+// row softmax of S [rows, L] fp32 (scaled) -> P bf16; one warp per row
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ S, bf16* __restrict__ P, int rows, int L,
+                                                           float scale) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* s = S + (long long)row * L;
+    float mx = -INFINITY;
+    for (int i = lane; i < L; i += 32) mx = fmaxf(mx, s[i]);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+    for (int i = lane; i < L; i += 32) sum += __expf((s[i] - mx) * scale);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float inv = 1.f / sum;
+    for (int i = lane; i < L; i += 32) P[(long long)row * L + i] = __float2bfloat16(__expf((s[i] - mx) * scale) * inv);
+}
+// conv weight (Cout, Cin, 3, 3) fp32 -> bf16 [Cout][ky][kx][Cin] (the K order of the implicit GEMM)
+__global__ void repack_conv3_kernel(const float* __restrict__ w, bf16* __restrict__ out, int Cout, int Cin) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)Cout * Cin * 9) return;
+    const int c = (int)(i % Cin);
+    const int tap = (int)((i / Cin) % 9);
+    const int o = (int)(i / ((long long)Cin * 9));
+    out[i] = __float2bfloat16(w[((long long)o * Cin + c) * 9 + tap]);
+}
+// b_out[o] = b_o[o] + sum_c W_o[o, c] * b_v[c]   (v's bias commutes with the softmax: rows of P sum to one)
+__global__ void fold_v_bias_kernel(const float* __restrict__ Wo, const float* __restrict__ bo, const float* __restrict__ bv,
+                                   float* __restrict__ out, int C) {
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= C) return;
+    float acc = bo[o];
+    for (int c = 0; c < C; ++c) acc = fmaf(Wo[(long long)o * C + c], bv[c], acc);
+    out[o] = acc;
+}
+
+struct VParam {
+    std::vector<int64_t> shape;
+    size_t n = 0;
+    float* d32 = nullptr;
+    bool set = false;
+};
+struct Conv3 {  // 3x3 convolution as implicit GEMM
+    bf16* w16 = nullptr;  // [Cout][9][Cin]
+    const float* b = nullptr;
+    int Cin = 0, Cout = 0;
+};
+struct Conv1 {  // 1x1 convolution as plain GEMM
+    bf16* w16 = nullptr;  // [Cout][Cin]
+    const float* b = nullptr;
+    int Cin = 0, Cout = 0;
+};
+struct ResBlock {
+    const float *n1w, *n1b, *n2w, *n2b;
+    Conv3 c1, c2;
+    Conv1 nin;
+    bool has_nin = false;
+    int Cin = 0, Cout = 0;
+};
+
+}  // namespace
+}  // namespace pdm
+
+using namespace pdm;
+
+struct pdm_vae {
+    pdm_vae_config cfg;
+    int nlev = 0;
+    std::map<std::string, VParam> params;
+    std::vector<void*> owned;  // derived device buffers
+    bool finalized = false;
+    // graph of layers
+    ResBlock mid1, mid2;
+    struct {
+        const float *nw, *nb;
+        Conv1 q, k, v, o;
+        float* bo_folded = nullptr;
+    } attn;
+    struct Level {
+        std::vector<ResBlock> blocks;
+        bool has_up = false;
+        Conv3 up;
+    };
+    std::vector<Level> up;  // index = i_level
+    // workspace (grown on demand)
+    size_t ws_bytes = 0;
+    uint8_t* ws = nullptr;
+
+    ~pdm_vae() {
+        for (auto& kv : params)
+            if (kv.second.d32) cudaFree(kv.second.d32);
+        for (void* p : owned) cudaFree(p);
+        if (ws) cudaFree(ws);
+    }
+    int ch_at(int level) const { return cfg.ch * cfg.ch_mult[level]; }
+
+    void expect(const std::string& k, std::vector<int64_t> shape) {
+        VParam p;
+        p.shape = shape;
+        p.n = 1;
+        for (auto s : shape) p.n *= (size_t)s;
+        params[k] = p;
+    }
+    void expect_res(const std::string& pre, int cin, int cout) {
+        expect(pre + "norm1.weight", {cin});
+        expect(pre + "norm1.bias", {cin});
+        expect(pre + "conv1.weight", {cout, cin, 3, 3});
+        expect(pre + "conv1.bias", {cout});
+        expect(pre + "norm2.weight", {cout});
+        expect(pre + "norm2.bias", {cout});
+        expect(pre + "conv2.weight", {cout, cout, 3, 3});
+        expect(pre + "conv2.bias", {cout});
+        if (cin != cout) {
+            expect(pre + "nin_shortcut.weight", {cout, cin, 1, 1});
+            expect(pre + "nin_shortcut.bias", {cout});
+        }
+    }
+    void declare() {
+        const int zc = cfg.z_channels, ed = cfg.embed_dim;
+        expect("post_quant_conv.weight", {zc, ed, 1, 1});
+        expect("post_quant_conv.bias", {zc});
+        int block_in = ch_at(nlev - 1);
+        expect("decoder.conv_in.weight", {block_in, zc, 3, 3});
+        expect("decoder.conv_in.bias", {block_in});
+        expect_res("decoder.mid.block_1.", block_in, block_in);
+        for (const char* n : {"q", "k", "v", "proj_out"}) {
+            expect(std::string("decoder.mid.attn_1.") + n + ".weight", {block_in, block_in, 1, 1});
+            expect(std::string("decoder.mid.attn_1.") + n + ".bias", {block_in});
+        }
+        expect("decoder.mid.attn_1.norm.weight", {block_in});
+        expect("decoder.mid.attn_1.norm.bias", {block_in});
+        expect_res("decoder.mid.block_2.", block_in, block_in);
+        for (int lev = nlev - 1; lev >= 0; --lev) {
+            const int block_out = ch_at(lev);
+            for (int i = 0; i <= cfg.num_res_blocks; ++i) {
+                expect_res("decoder.up." + std::to_string(lev) + ".block." + std::to_string(i) + ".", block_in, block_out);
+                block_in = block_out;
+            }
+            if (lev != 0) {
+                expect("decoder.up." + std::to_string(lev) + ".upsample.conv.weight", {block_in, block_in, 3, 3});
+                expect("decoder.up." + std::to_string(lev) + ".upsample.conv.bias", {block_in});
+            }
+        }
+        expect("decoder.norm_out.weight", {block_in});
+        expect("decoder.norm_out.bias", {block_in});
+        expect("decoder.conv_out.weight", {cfg.out_ch, block_in, 3, 3});
+        expect("decoder.conv_out.bias", {cfg.out_ch});
+    }
+    static bool ignorable(const std::string& k) {
+        return k.rfind("encoder.", 0) == 0 || k.rfind("quant_conv.", 0) == 0 || k.rfind("loss.", 0) == 0;
+    }
+    void set_param(const std::string& key, const void* dev, const int64_t* shape, int ndim, cudaStream_t s) {
+        if (ignorable(key)) return;  // the sampling path only decodes
+        auto it = params.find(key);
+        PDM_REQUIRE(it != params.end(), "unexpected state_dict key '" + key + "'");
+        VParam& p = it->second;
+        bool ok = (int)p.shape.size() == ndim;
+        for (int i = 0; ok && i < ndim; ++i) ok = p.shape[i] == shape[i];
+        PDM_REQUIRE(ok, "size mismatch for " + key);
+        if (!p.d32) PDM_CHECK_CUDA(cudaMalloc(&p.d32, p.n * sizeof(float)));
+        PDM_CHECK_CUDA(cudaMemcpyAsync(p.d32, dev, p.n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        p.set = true;
+        finalized = false;
+    }
+    template <typename T>
+    T* dev_alloc(size_t n) {
+        void* p = nullptr;
+        PDM_CHECK_CUDA(cudaMalloc(&p, n * sizeof(T)));
+        owned.push_back(p);
+        return (T*)p;
+    }
+    Conv3 conv3(const std::string& pre, int cin, int cout, cudaStream_t s) {
+        Conv3 c;
+        c.Cin = cin; c.Cout = cout;
+        c.b = params.at(pre + "bias").d32;
+        c.w16 = dev_alloc<bf16>((size_t)cout * cin * 9);
+        const long long n = (long long)cout * cin * 9;
+        repack_conv3_kernel<<<(unsigned)ceil_div_ll(n, 256), 256, 0, s>>>(params.at(pre + "weight").d32, c.w16, cout, cin);
+        check_launch("repack_conv3");
+        return c;
+    }
+    Conv1 conv1(const std::string& pre, int cin, int cout, cudaStream_t s) {
+        Conv1 c;
+        c.Cin = cin; c.Cout = cout;
+        c.b = params.at(pre + "bias").d32;
+        c.w16 = dev_alloc<bf16>((size_t)cout * cin);
+        convert_f32_bf16(params.at(pre + "weight").d32, c.w16, (long long)cout * cin, s);
+        return c;
+    }
+    ResBlock res(const std::string& pre, int cin, int cout, cudaStream_t s) {
+        ResBlock r;
+        r.Cin = cin; r.Cout = cout;
+        r.n1w = params.at(pre + "norm1.weight").d32; r.n1b = params.at(pre + "norm1.bias").d32;
+        r.n2w = params.at(pre + "norm2.weight").d32; r.n2b = params.at(pre + "norm2.bias").d32;
+        r.c1 = conv3(pre + "conv1.", cin, cout, s);
+        r.c2 = conv3(pre + "conv2.", cout, cout, s);
+        r.has_nin = cin != cout;
+        if (r.has_nin) r.nin = conv1(pre + "nin_shortcut.", cin, cout, s);
+        return r;
+    }
+    void finalize(cudaStream_t s) {
+        std::string missing;
+        int nmiss = 0;
+        for (auto& kv : params)
+            if (!kv.second.set) {
+                if (nmiss < 6) missing += kv.first + " ";
+                ++nmiss;
+            }
+        PDM_REQUIRE(nmiss == 0, "missing " + std::to_string(nmiss) + " state_dict keys: " + missing);
+        for (void* p : owned) cudaFree(p);
+        owned.clear();
+        clear_tmap_cache_all();
+        int block_in = ch_at(nlev - 1);
+        mid1 = res("decoder.mid.block_1.", block_in, block_in, s);
+        mid2 = res("decoder.mid.block_2.", block_in, block_in, s);
+        attn.nw = params.at("decoder.mid.attn_1.norm.weight").d32;
+        attn.nb = params.at("decoder.mid.attn_1.norm.bias").d32;
+        attn.q = conv1("decoder.mid.attn_1.q.", block_in, block_in, s);
+        attn.k = conv1("decoder.mid.attn_1.k.", block_in, block_in, s);
+        attn.v = conv1("decoder.mid.attn_1.v.", block_in, block_in, s);
+        attn.o = conv1("decoder.mid.attn_1.proj_out.", block_in, block_in, s);
+        attn.bo_folded = dev_alloc<float>(block_in);
+        fold_v_bias_kernel<<<ceil_div(block_in, 128), 128, 0, s>>>(params.at("decoder.mid.attn_1.proj_out.weight").d32, attn.o.b,
+                                                                  attn.v.b, attn.bo_folded, block_in);
+        check_launch("fold_v_bias");
+        up.assign(nlev, Level());
+        for (int lev = nlev - 1; lev >= 0; --lev) {
+            const int block_out = ch_at(lev);
+            for (int i = 0; i <= cfg.num_res_blocks; ++i) {
+                up[lev].blocks.push_back(
+                    res("decoder.up." + std::to_string(lev) + ".block." + std::to_string(i) + ".", block_in, block_out, s));
+                block_in = block_out;
+            }
+            if (lev != 0) {
+                up[lev].has_up = true;
+                up[lev].up = conv3("decoder.up." + std::to_string(lev) + ".upsample.conv.", block_in, block_in, s);
+            }
+        }
+        PDM_CHECK_CUDA(cudaStreamSynchronize(s));
+        finalized = true;
+    }
+    static void clear_tmap_cache_all();
+
+    // ------------------------------------------------------------------ workspace
+    struct Buf {
+        float *X, *X2, *H1, *S;   // residual stream, its alternate (shortcut / upsample output), conv1 output, attention scores
+        bf16 *A16, *Q, *K, *VT, *P, *O;
+        float* part;  // GroupNorm partial sums [n][slabs][32][2]
+        float* mr;
+    };
+    size_t max_act_elems(int n, int h0) const {  // largest [pixels, C] activation of the decoder for latent side h0
+        size_t mx = 0;
+        int side = h0, block_in = ch_at(nlev - 1);
+        for (int lev = nlev - 1; lev >= 0; --lev) {
+            mx = std::max(mx, (size_t)n * side * side * std::max(block_in, ch_at(lev)));
+            block_in = ch_at(lev);
+            if (lev != 0) {
+                side *= 2;
+                mx = std::max(mx, (size_t)n * side * side * block_in);
+            }
+        }
+        return mx;
+    }
+    Buf carve(int n, int h0, bool dry, size_t* total) {
+        const size_t act = max_act_elems(n, h0);
+        const size_t tok = (size_t)h0 * h0, C = ch_at(nlev - 1);
+        size_t off = 0;
+        auto take = [&](size_t bytes) -> void* {
+            off = (off + 255) & ~size_t(255);
+            void* p = dry ? nullptr : ws + off;
+            off += bytes;
+            return p;
+        };
+        Buf b;
+        b.X = (float*)take(act * 4);
+        b.X2 = (float*)take(act * 4);
+        b.H1 = (float*)take(act * 4);
+        b.A16 = (bf16*)take(act * 2);
+        b.Q = (bf16*)take((size_t)n * tok * C * 2);
+        b.K = (bf16*)take((size_t)n * tok * C * 2);
+        b.O = (bf16*)take((size_t)n * tok * C * 2);
+        b.VT = (bf16*)take(tok * C * 2);
+        b.S = (float*)take(tok * tok * 4);
+        b.P = (bf16*)take(tok * tok * 2);
+        {
+            int side = h0;
+            for (int lev = nlev - 1; lev > 0; --lev) side *= 2;
+            b.part = (float*)take((size_t)n * ceil_div(side * side, GN_PPB) * GN_GROUPS * 2 * 4);
+        }
+        b.mr = (float*)take((size_t)n * GN_GROUPS * 2 * 4);
+        *total = off + 256;
+        return b;
+    }
+    Buf workspace(int n, int h0) {
+        size_t need = 0;
+        carve(n, h0, true, &need);
+        if (need > ws_bytes) {
+            PDM_CHECK_CUDA(cudaDeviceSynchronize());
+            if (ws) cudaFree(ws);
+            ws = nullptr;
+            ws_bytes = 0;
+            clear_tmap_cache_all();
+            PDM_CHECK_CUDA(cudaMalloc(&ws, need));
+            ws_bytes = need;
+        }
+        return carve(n, h0, false, &need);
+    }
+
+    // ------------------------------------------------------------------ layers
+    void group_norm(const Buf& b, const float* x, const float* gw, const float* gb, bf16* out, int n, int hw, int C, bool act,
+                    cudaStream_t s) {
+        PDM_REQUIRE(C % (GN_GROUPS * 4) == 0 && C <= 1024, "GroupNorm: channels must be a multiple of 128 and <= 1024");
+        const int nblk = ceil_div(hw, GN_PPB);
+        gn_stats_kernel<<<dim3(nblk, n), 256, 0, s>>>(x, b.part, hw, C, GN_PPB);
+        check_launch("gn_stats");
+        gn_finalize_kernel<<<ceil_div(n * GN_GROUPS, 128), 128, 0, s>>>(b.part, b.mr, n, nblk, (double)hw * (C / GN_GROUPS), 1e-6f);
+        check_launch("gn_finalize");
+        const long long total4 = (long long)n * hw * C / 4;
+        const int grid = (int)std::min<long long>(ceil_div_ll(total4, 256), 148 * 16);
+        gn_apply_kernel<<<grid, 256, 0, s>>>(x, b.mr, gw, gb, out, total4, hw, C, act ? 1 : 0);
+        check_launch("gn_apply");
+    }
+    // out32 (+= if accumulate) = conv3x3(a16) + bias
+    void conv3_gemm(const Conv3& c, const bf16* a16, float* out32, bool accumulate, int n, int H, int W, cudaStream_t s) {
+        GemmProblem g;
+        g.A1 = a16; g.K1 = 9 * c.Cin; g.W16 = c.w16; g.bias = c.b; g.N = c.Cout;
+        g.nb = 1; g.Lr = n * H * W;
+        g.out32 = out32;
+        if (accumulate) g.resid = out32;
+        g.conv_N = n; g.conv_H = H; g.conv_W = W; g.conv_C = c.Cin;
+        gemm_tc_bf16(g, s);
+    }
+    void conv1_gemm(const Conv1& c, const bf16* a16, const float* bias, float* out32, bool accumulate, bf16* out16, long long rows,
+                    cudaStream_t s) {
+        GemmProblem g;
+        g.A1 = a16; g.K1 = c.Cin; g.W16 = c.w16; g.bias = bias; g.N = c.Cout;
+        g.nb = 1; g.Lr = (int)rows;
+        g.out32 = out32; g.out2 = out16;
+        if (accumulate) g.resid = out32;
+        gemm_tc_bf16(g, s);
+    }
+    void to_bf16(const float* x, bf16* out, int n, int H, int W, int C, bool upsample, cudaStream_t s) {
+        const long long total4 = (long long)n * H * W * C / 4 * (upsample ? 4 : 1);
+        const int grid = (int)std::min<long long>(ceil_div_ll(total4, 256), 148 * 16);
+        convert_up_kernel<<<grid, 256, 0, s>>>(x, out, total4, H, W, C, upsample ? 1 : 0);
+        check_launch("convert_up");
+    }
+    // x (b.X, [n, hw, Cin]) -> b.X ([n, hw, Cout])        (libs/autoencoder.py:114-134)
+    void res_block(const ResBlock& r, Buf& b, int n, int H, int W, cudaStream_t s) {
+        const int hw = H * W;
+        group_norm(b, b.X, r.n1w, r.n1b, b.A16, n, hw, r.Cin, true, s);
+        conv3_gemm(r.c1, b.A16, b.H1, false, n, H, W, s);
+        if (r.has_nin) {  // x = nin_shortcut(x): 1x1 on the raw stream
+            to_bf16(b.X, b.A16, n, H, W, r.Cin, false, s);
+            conv1_gemm(r.nin, b.A16, r.nin.b, b.X2, false, nullptr, (long long)n * hw, s);
+            std::swap(b.X, b.X2);
+        }
+        group_norm(b, b.H1, r.n2w, r.n2b, b.A16, n, hw, r.Cout, true, s);
+        conv3_gemm(r.c2, b.A16, b.X, true, n, H, W, s);
+    }
+    // x += proj_out(attention(norm(x)))                    (libs/autoencoder.py:171-195)
+    void attn_block(Buf& b, int n, int H, int W, cudaStream_t s) {
+        const int L = H * W, C = attn.q.Cin;
+        group_norm(b, b.X, attn.nw, attn.nb, b.A16, n, L, C, false, s);
+        conv1_gemm(attn.q, b.A16, attn.q.b, nullptr, false, b.Q, (long long)n * L, s);
+        conv1_gemm(attn.k, b.A16, attn.k.b, nullptr, false, b.K, (long long)n * L, s);
+        const float scale = 1.f / sqrtf((float)C);
+        for (int i = 0; i < n; ++i) {
+            const bf16* hn = b.A16 + (size_t)i * L * C;
+            {  // V^T [C, L] = W_v . hn^T  (roles of weight and activation swapped; the bias is folded into proj_out)
+                GemmProblem g;
+                g.A1 = attn.v.w16; g.K1 = C; g.W16 = hn; g.N = L; g.nb = 1; g.Lr = C; g.out2 = b.VT;
+                gemm_tc_bf16(g, s);
+            }
+            {  // S [L, L] = q k^T
+                GemmProblem g;
+                g.A1 = b.Q + (size_t)i * L * C; g.K1 = C; g.W16 = b.K + (size_t)i * L * C; g.N = L; g.nb = 1; g.Lr = L;
+                g.out32 = b.S;
+                gemm_tc_bf16(g, s);
+            }
+            softmax_rows_kernel<<<ceil_div(L, 8), 256, 0, s>>>(b.S, b.P, L, L, scale);
+            check_launch("softmax_rows");
+            {  // O [L, C] = P V
+                GemmProblem g;
+                g.A1 = b.P; g.K1 = L; g.W16 = b.VT; g.N = C; g.nb = 1; g.Lr = L; g.out2 = b.O + (size_t)i * L * C;
+                gemm_tc_bf16(g, s);
+            }
+        }
+        conv1_gemm(attn.o, b.O, attn.bo_folded, b.X, true, nullptr, (long long)n * L, s);
+    }
+
+    void decode(const float* z, float* out, int n, int h0, cudaStream_t s) {
+        PDM_REQUIRE(finalized, "VAE parameters not finalized");
+        PDM_REQUIRE(cfg.z_channels == 4 && cfg.embed_dim == 4, "VAE: z_channels = embed_dim = 4 expected");
+        PDM_REQUIRE((h0 * h0) % 128 == 0 && (h0 >= 128 ? h0 % 128 == 0 : 128 % h0 == 0), "VAE: latent side must be 16, 32, 64, ...");
+        Buf b = workspace(n, h0);
+        int H = h0, W = h0;
+        const int C0 = ch_at(nlev - 1);
+        {
+            const long long total = (long long)n * H * W * (C0 / 4);
+            conv_in_kernel<4><<<(unsigned)ceil_div_ll(total, 128), 128, 0, s>>>(
+                z, params.at("post_quant_conv.weight").d32, params.at("post_quant_conv.bias").d32,
+                params.at("decoder.conv_in.weight").d32, params.at("decoder.conv_in.bias").d32, b.X, n, H, W, C0,
+                1.f / cfg.scale_factor);
+            check_launch("vae_conv_in");
+        }
+        res_block(mid1, b, n, H, W, s);
+        attn_block(b, n, H, W, s);
+        res_block(mid2, b, n, H, W, s);
+        for (int lev = nlev - 1; lev >= 0; --lev) {
+            for (auto& r : up[lev].blocks) res_block(r, b, n, H, W, s);
+            if (up[lev].has_up) {  // nearest 2x + 3x3 conv (libs/autoencoder.py:46-50)
+                const int C = up[lev].up.Cin;
+                to_bf16(b.X, b.A16, n, H, W, C, true, s);
+                H *= 2; W *= 2;
+                conv3_gemm(up[lev].up, b.A16, b.X2, false, n, H, W, s);
+                std::swap(b.X, b.X2);
+            }
+        }
+        const int Cl = ch_at(0);
+        group_norm(b, b.X, params.at("decoder.norm_out.weight").d32, params.at("decoder.norm_out.bias").d32, b.A16, n, H * W, Cl,
+                   true, s);
+        PDM_REQUIRE(cfg.out_ch <= 4 && Cl % 8 == 0, "VAE: out_ch <= 4");
+        conv_out_kernel<<<(unsigned)ceil_div_ll((long long)n * H * W, 128), 128, 9 * Cl * 4 * sizeof(float), s>>>(
+            b.A16, params.at("decoder.conv_out.weight").d32, params.at("decoder.conv_out.bias").d32, out, n, H, W, Cl, cfg.out_ch);
+        check_launch("vae_conv_out");
+    }
+};
+
+namespace pdm {
+void clear_tmap_cache();
+}
+void pdm_vae::clear_tmap_cache_all() { pdm::clear_tmap_cache(); }
+
+namespace {
+template <typename F>
+int vguard(F&& f) {
+    try {
+        f();
+        return 0;
+    } catch (const std::exception& e) {
+        set_last_error(e.what());
+        return 1;
+    } catch (...) {
+        set_last_error("unknown error");
+        return 1;
+    }
+}
+}  // namespace
+
+extern "C" {
+
+int pdm_vae_create(const pdm_vae_config* c, pdm_vae_handle* out) {
+    return vguard([&] {
+        PDM_REQUIRE(c && out, "null argument");
+        int ndev = 0;
+        PDM_REQUIRE(cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0, "no CUDA device: libpdm has no CPU path");
+        PDM_REQUIRE(c->num_levels >= 1 && c->num_levels <= 8 && c->ch % 32 == 0 && c->num_res_blocks >= 1, "bad VAE config");
+        std::unique_ptr<pdm_vae> h(new pdm_vae());
+        h->cfg = *c;
+        h->nlev = c->num_levels;
+        for (int i = 0; i < c->num_levels; ++i) PDM_REQUIRE((c->ch * c->ch_mult[i]) % 128 == 0, "VAE: every level needs C % 128 == 0");
+        h->declare();
+        *out = h.release();
+    });
+}
+int pdm_vae_destroy(pdm_vae_handle h) {
+    return vguard([&] {
+        if (h) {
+            cudaDeviceSynchronize();
+            delete h;
+        }
+    });
+}
+int pdm_vae_set_param(pdm_vae_handle h, const char* key, const void* dev_f32, const int64_t* shape, int32_t ndim, void* stream) {
+    return vguard([&] {
+        PDM_REQUIRE(h && key && dev_f32 && shape, "null argument");
+        h->set_param(key, dev_f32, shape, ndim, (cudaStream_t)stream);
+    });
+}
+int pdm_vae_finalize_params(pdm_vae_handle h, void* stream) {
+    return vguard([&] {
+        PDM_REQUIRE(h, "null handle");
+        h->finalize((cudaStream_t)stream);
+    });
+}
+int pdm_vae_decode(pdm_vae_handle h, const float* z, float* out, int32_t n, int32_t latent_size, void* stream) {
+    return vguard([&] {
+        PDM_REQUIRE(h && z && out && n > 0 && latent_size > 0, "bad argument");
+        h->decode(z, out, n, latent_size, (cudaStream_t)stream);
+    });
+}
+int pdm_vae_workspace_bytes(pdm_vae_handle h, int32_t n, int32_t latent_size, size_t* bytes) {
+    return vguard([&] {
+        PDM_REQUIRE(h && bytes && n > 0, "bad argument");
+        h->carve(n, latent_size, true, bytes);
+    });
+}
+
+}  // extern "C"

@@ -6,13 +6,18 @@ Mirrors the live wiring of the reference (``train_t2i_discrete.py:480-546`` eval
     config file  ->  nnet from ``<ckpt_root>/<step>.ckpt/nnet_ema.pth``  ->  contexts  ->  JointSampler (libpdm)
                  ->  all-gather over ranks  ->  latents ``.pt`` + panoptic label PNGs (``bits2int`` + ``color_map``)
 
-CLIP text encoding and the VAE decode run once per sample OUTSIDE the loop in the reference (``libs/clip.py``,
-``libs/autoencoder.py``): their weights are not part of this tree, so contexts come from the extracted-feature cache
-(``datasets.py:577-613``) or from ``--synthetic``, and ``decode`` is an optional callable
-``(z [B,4,h,w]) -> images [B,3,H,W]`` the caller passes in (the reference's ``decode_large_batch``).
+Either side of the loop (both run once per sample, outside it):
+  * contexts: ``--prompts FILE`` (one caption per line) through ``libs.clip.FrozenCLIPEmbedder`` (``libs/clip.py:13-38``: the
+    Hugging Face CLIP text model, as in the reference; ``--clip`` names a hub id or a local directory), or the
+    extracted-feature cache (``--features``, ``datasets.py:577-613``), or ``--synthetic``;
+  * images: ``--autoencoder autoencoder_kl.pth`` decodes the latents on the GPU with libpdm's VAE decoder
+    (``libs.autoencoder``, csrc/vae.cu; the reference's ``decode_large_batch``, ``eval_t2i_discrete.py:74-84``) and writes
+    ``<out>/{i}.png`` after ``unpreprocess`` (``0.5 (x + 1)`` clamped, ``datasets.py``).  The weights of both models are not part
+    of this tree (no network): without them the driver still writes latents and panoptic label maps.
 
     python -m panopticdiffusionmodels_b200.sample_t2i --config mscoco_uvit_small --ckpt-root ckpts \\
-           --features assets/datasets/coco256_features --out samples --n-samples 64
+           --features assets/datasets/coco256_features --autoencoder assets/stable-diffusion/autoencoder_kl.pth \\
+           --out samples --n-samples 64
     torchrun --nproc-per-node 8 -m panopticdiffusionmodels_b200.sample_t2i ...     # one rank per GPU, batch sharded
 """
 from __future__ import annotations
@@ -73,11 +78,22 @@ def sample_to_dir(nnet, config, contexts_fn: Callable[[int], torch.Tensor], empt
             for i in range(lab.shape[0]):
                 ck.save_mask_png(lab[i], os.path.join(mask_dir, f"{i}.png"), cm)
         if decode is not None:
-            from torchvision.utils import save_image
-            imgs = decode(z)
+            imgs = unpreprocess(decode(z))
             for i in range(imgs.shape[0]):
-                save_image(imgs[i].cpu(), os.path.join(out_dir, f"{i}.png"))
+                ck.save_image_png(imgs[i], os.path.join(out_dir, f"{i}.png"))
     return z, pm, labels
+
+
+def unpreprocess(v: torch.Tensor) -> torch.Tensor:
+    """[-1, 1] -> [0, 1], clamped (datasets.py ``DatasetFactory.unpreprocess``)."""
+    return (0.5 * (v + 1.0)).clamp_(0.0, 1.0)
+
+
+def context_indices(batch_index: int, mini_batch_size: int, rank: int, n_ranks: int, total: int):
+    """Dataset rows for this rank's mini-batch number ``batch_index``: CONTIGUOUS per-rank blocks inside each global batch, so
+    that after the rank-major all-gather sample ``i`` of the output belongs to caption ``i`` of the dataset."""
+    base = batch_index * mini_batch_size * n_ranks + rank * mini_batch_size
+    return [(base + i) % total for i in range(mini_batch_size)]
 
 
 def main(argv=None):
@@ -87,6 +103,9 @@ def main(argv=None):
     ap.add_argument("--nnet-path", default=None)
     ap.add_argument("--features", default=None, help="extracted-feature directory (val2017/ + empty_context.npy)")
     ap.add_argument("--synthetic", action="store_true", help="random contexts (no feature cache at hand)")
+    ap.add_argument("--prompts", default=None, help="text file, one caption per line -> CLIP text encoder (libs.clip)")
+    ap.add_argument("--clip", default="openai/clip-vit-large-patch14", help="hub id or local directory of the CLIP text model")
+    ap.add_argument("--autoencoder", default=None, help="autoencoder_kl.pth: decode the latents to PNGs with libpdm's VAE decoder")
     ap.add_argument("--out", default="samples")
     ap.add_argument("--n-samples", type=int, default=None)
     ap.add_argument("--mini-batch-size", type=int, default=None)
@@ -109,21 +128,37 @@ def main(argv=None):
     gen = torch.Generator(device=dev).manual_seed(rank_seed(config.seed))   # seed + rank (train_t2i_discrete.py:237)
     nnet = build_nnet(config, dev, a.ckpt_root, a.nnet_path, a.precision)
     use_panoptic = bool(config.nnet.get("enable_panoptic", True))
-    if a.features and not a.synthetic:
-        cache = ck.FeatureCache(os.path.join(a.features, "val2017"))
-        empty = ck.load_empty_context(a.features).to(dev)
-        cursor = [rank]
+    calls = [0]
+    if a.prompts:
+        from .libs.clip import FrozenCLIPEmbedder
+        clip = FrozenCLIPEmbedder(a.clip, device=dev).to(dev)
+        prompts = [ln.strip() for ln in open(a.prompts) if ln.strip()]
+        n_samples = a.n_samples or len(prompts)
+        empty = clip.encode([""])[0].float()           # the reference's empty_context (scripts/extract_empty_feature.py)
 
         def contexts_fn(b):
-            _, n = world()
-            idx = [(cursor[0] + i * n) % len(cache) for i in range(b)]
-            cursor[0] += b * n
+            idx = context_indices(calls[0], b, rank, world()[1], len(prompts))
+            calls[0] += 1
+            return clip.encode([prompts[i] for i in idx]).float()
+    elif a.features and not a.synthetic:
+        cache = ck.FeatureCache(os.path.join(a.features, "val2017"))
+        empty = ck.load_empty_context(a.features).to(dev)
+
+        def contexts_fn(b):
+            idx = context_indices(calls[0], b, rank, world()[1], len(cache))
+            calls[0] += 1
             return cache.contexts(idx).to(dev)
     else:
         T, cd = int(config.nnet.get("num_clip_token", 77)), int(config.nnet.get("clip_dim", 768))
         empty = torch.randn(T, cd, device=dev, generator=gen)
         contexts_fn = lambda b: torch.randn(b, T, cd, device=dev, generator=gen)  # noqa: E731
-    sample_to_dir(nnet, config, contexts_fn, empty, a.out, n_samples, mbs, use_panoptic=use_panoptic, generator=gen)
+    decode = None
+    if a.autoencoder:
+        from .libs import autoencoder as ae
+        vae = ae.get_model(a.autoencoder, scale_factor=float(config.autoencoder.get("scale_factor", 0.18215))).to(dev)
+        decode = vae.decode                              # chunked inside (decode_large_batch, eval_t2i_discrete.py:74-84)
+    sample_to_dir(nnet, config, contexts_fn, empty, a.out, n_samples, mbs, use_panoptic=use_panoptic, decode=decode,
+                  generator=gen)
     if dist.is_initialized():
         dist.barrier()
         dist.destroy_process_group()

@@ -129,3 +129,19 @@ def test_module_copies_do_not_share_the_engine_handle():
             assert set(dup.state_dict()) == set(net.state_dict())
     finally:
         net._handle = None                    # do not hand the fake pointer to pdm_destroy
+
+
+def test_vae_state_dict_layout_matches_reference():
+    """libs.autoencoder.FrozenAutoencoderKL holds exactly the reference module's parameters (keys and shapes recorded from the
+    reference's own state_dict by tests/golden/make_vae.py, whose get_model also loaded ours with its no-missing /
+    no-unexpected assertion) and refuses to run without a CUDA device."""
+    import json
+    from panopticdiffusionmodels_b200.libs.autoencoder import get_model
+    want = json.load(open(os.path.join(ROOT, "tests", "golden", "vae_keys.json")))
+    vae = get_model(None, 0.23010)
+    mine = {k: list(v.shape) for k, v in vae.state_dict().items()}
+    assert mine == want
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        vae.decode(torch.zeros(1, 4, 16, 16))
+    with pytest.raises(NotImplementedError):
+        vae.encode(torch.zeros(1, 3, 128, 128))

@@ -134,3 +134,20 @@ def test_full_depth_forward_matches_reference(tag):
     rn, ry = torch.from_numpy(ref[f"{tag}/noise"]), torch.from_numpy(ref[f"{tag}/y"])
     assert (noise - rn).abs().max() <= 2e-5 * rn.abs().max(), float((noise - rn).abs().max() / rn.abs().max())
     assert (y - ry).abs().max() <= 2e-5 * max(1.0, float(ry.abs().max()))
+
+
+def test_vae_decode_matches_reference():
+    """oracle/vae_oracle.py against the REAL reference's FrozenAutoencoderKL.decode (tests/golden/make_vae.py): SD autoencoder
+    layout, random weights rebuilt from the seed, 2 latents of 16 x 16 -> 128 x 128 px."""
+    from oracle import vae_oracle
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_vae import SCALE, build_vae, latents
+    ref = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "vae_decode.npz"))
+    vae = build_vae()
+    sd = {k: v.detach().clone() for k, v in vae.state_dict().items()}
+    torch.set_num_threads(os.cpu_count())
+    with torch.no_grad():
+        out = vae_oracle.vae_decode(sd, vae.ddconfig, latents(), SCALE)
+    want = torch.from_numpy(ref["out"])
+    assert out.shape == want.shape
+    assert (out - want).abs().max() <= 2e-5 * want.abs().max()

@@ -134,7 +134,7 @@ def test_multistep_plan_matches_reference_updates():
 def test_c_planner_matches_host_planner(method, order, steps, mask_opt, skip_type):
     """pdm_solver_plan (C ABI host planner, csrc/plan.cu) against the Python host planner, whose float32 torch ops are what the
     reference evaluates.  Structure (stages, flags, orders, record kinds) is identical; every coefficient agrees to <= 4e-6
-    relative (+ 2e-7 absolute; 3e-4 for the two ill-conditioned 3M coefficients): the residue is libm-vs-SLEEF rounding of exp / log / log1p / expm1 and torch.linspace's
+    relative (+ 2e-7 absolute; 3e-5 / 3e-4 for the ill-conditioned difference-term coefficients): the residue is libm-vs-SLEEF rounding of exp / log / log1p / expm1 and torch.linspace's
     per-SIMD-chunk rounding, amplified where a coefficient is a difference of nearby numbers."""
     from panopticdiffusionmodels_b200 import dpm_solver_pp as P
     from panopticdiffusionmodels_b200.multistep import build_multistep_plan
@@ -154,6 +154,10 @@ def test_c_planner_matches_host_planner(method, order, steps, mask_opt, skip_typ
     assert np.array_equal(got[:, 13:15], want[:, 13:15])
     err = np.abs(got.astype(np.float64) - want.astype(np.float64))
     tol = 4e-6 * np.abs(want.astype(np.float64)) + 2e-7
+    if method != "multistep":
+        # the difference-term coefficients carry phi_22 = expm1(-r2 h) / (r2 h) + 1 and phi_2 = expm1(-h) / h + 1, which cancel
+        # to O(h): an ulp of expm1 is amplified by ~2 / h (small steps of the 'logSNR' / 't2' grids)
+        tol[:, [5, 7]] = 3e-5 * np.abs(want[:, [5, 7]].astype(np.float64)) + 2e-7
     if method == "multistep":
         # the 3M coefficients (e^-h - 1) / h + 1 and (e^-h - 1 + h) / h^2 - 1/2 cancel to O(h): a float32 ulp of e^-h is
         # amplified by 1 / h .. 1 / h^2 -- in the reference's own arithmetic as much as here
