@@ -115,6 +115,9 @@ struct GemmProblem {
     // (gamma * W, centred along K) and `bias` holds bias + W.beta, so that out = rstd * acc + bias == LN(x).W^T + b
     const float* ln_rstd = nullptr;  // [rows] 1 / sqrt(var + eps) of x, from ln_rstd() over the producer's row sums
     int ln_rstd_bs = 0;
+    // plain fp32-output form only (no residual, no copies): ln_rstd is honoured there too (out = rstd * acc + bias), and
+    // rowbias [Lr, N] (fp32) is added per ROW OF THE BATCH after the bias (positional embedding of the patch-embed GEMM)
+    const float* rowbias = nullptr;
     // ---- implicit-GEMM 3x3 convolution, stride 1, zero padding 1 (tcgen05 kernel only; VAE decoder, vae.cu) ----
     // conv_H > 0: A1 is an NHWC activation [conv_N, conv_H, conv_W, conv_C] (bf16), rows = output pixels in (n, h, w) order
     // (Lr = conv_N * conv_H * conv_W, nb = 1), K1 = 9 * conv_C with k = (ky * 3 + kx) * conv_C + c, W16 = [N, 9 * conv_C].
@@ -191,6 +194,11 @@ struct HeadArgs {
     int nb, C, Cm, S, p, D;
 };
 void head_decode(const HeadArgs& a, cudaStream_t s);
+// bf16 engine path: patches -> bf16 GEMM operand rows, and the 3x3 heads on token-major decoder outputs
+void im2col_patches(const float* img, bf16* out, int Bx, int nb, int C, int S, int p, cudaStream_t s);
+void embed_extras(const EmbedArgs& a, cudaStream_t s);
+void conv3x3_tokens(const float* tok, const float* w, const float* bias, float* out, int nb, int C, int S, int p, int do_tanh,
+                    cudaStream_t s);
 
 struct UpdateArgs {
     const float* eps_c;

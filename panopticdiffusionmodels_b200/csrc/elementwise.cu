@@ -375,6 +375,40 @@ void transpose_f32(const float* in, float* out, int R, int Cc, cudaStream_t s) {
     check_launch("transpose");
 }
 
+// ---- bf16 engine path: the patch embedding runs on the tcgen05 GEMM kernel (gemm_tc.cu, plain fp32 form + per-row
+// positional table).  Patches become bf16 operand rows in the weight's K order (c, p1, p2); every fp32 pixel is split into
+// hi + lo bf16 halves ([hi | lo], K = 2 C p^2, against [W | W]) so that the solver state enters the network with 16
+// mantissa bits instead of 8 -- the identity path of the residual stream carries the embedding to the decoder.
+__global__ void __launch_bounds__(256) im2col_patch_kernel(const float* __restrict__ img, bf16* __restrict__ out, int Bx, int nb,
+                                                           int C, int S, int p) {
+    const int g = S / p, P = g * g, pp = p * p, kk = C * pp;
+    const long long total = (long long)nb * P * kk;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < total; i += stride) {
+        const int k = (int)(i % kk);
+        const long long row = i / kk;
+        const int pidx = (int)(row % P);
+        const int b = (int)(row / P), bi = b % Bx;
+        const int ph = pidx / g, pw = pidx % g;
+        const int c = k / pp, r = k % pp;
+        const float v = __ldg(img + (((long long)bi * C + c) * S + ph * p + r / p) * S + pw * p + r % p);
+        const bf16 hi = __float2bfloat16_rn(v);
+        out[row * (2 * kk) + k] = hi;
+        out[row * (2 * kk) + kk + k] = __float2bfloat16_rn(v - __bfloat162float(hi));
+    }
+}
+void im2col_patches(const float* img, bf16* out, int Bx, int nb, int C, int S, int p, cudaStream_t s) {
+    const long long total = (long long)nb * (S / p) * (S / p) * C * p * p;
+    const int grid = (int)std::min<long long>(ceil_div_ll(total, 256), 148 * 16);
+    im2col_patch_kernel<<<grid, 256, 0, s>>>(img, out, Bx, nb, C, S, p);
+    check_launch("im2col_patches");
+}
+void embed_extras(const EmbedArgs& a, cudaStream_t s) {
+    embed_extras_kernel<<<dim3(1 + a.T, a.nb), 128, 0, s>>>(a);
+    check_launch("embed_extras");
+}
+
 void embed_tokens(const EmbedArgs& a, cudaStream_t s) {
     const int kmax = std::max(a.C, a.mask ? a.Cm : 0) * a.p * a.p;
     PDM_REQUIRE(kmax <= 64, "embed: patch dimension > 64 unsupported");
@@ -594,6 +628,63 @@ __global__ void __launch_bounds__(256) conv3x3_kernel(const float* __restrict__ 
         }
     }
     out[idx] = do_tanh ? tanhf(acc) : acc;
+}
+
+// 3x3 head on TOKEN-MAJOR decoder outputs (bf16 engine path: decoder_pred runs on the GEMM kernel and leaves
+// tok [nb * P, p * p * C]; feature (p1 * p + p2) * C + c of patch (ph, pw) is pixel (ph p + p1, pw p + p2) of channel c,
+// libs/uvit_t2i.py:50) -- unpatchify is the gather of this kernel.  One thread = one pixel, ALL C output channels: the 9
+// neighbours are 9 contiguous C-float vectors (float4 loads), 9 C^2 FMAs against weights staged in shared memory as
+// [tap][ci][co]; stores are coalesced along x per output channel.
+template <int C>
+__global__ void __launch_bounds__(256) conv3x3_tok_kernel(const float* __restrict__ tok, const float* __restrict__ w,
+                                                          const float* __restrict__ bias, float* __restrict__ out, int nb, int S,
+                                                          int p, int do_tanh) {
+    __shared__ __align__(16) float wsm[9 * C * C];
+    for (int i = threadIdx.x; i < 9 * C * C; i += blockDim.x) {
+        const int co = i % C, ci = (i / C) % C, tap = i / (C * C);
+        wsm[i] = w[((long long)co * C + ci) * 9 + tap];  // [co][ci][3][3] -> [tap][ci][co]
+    }
+    __syncthreads();
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)nb * S * S) return;
+    const int x = (int)(idx % S), y = (int)((idx / S) % S);
+    const long long b = idx / ((long long)S * S);
+    const int g = S / p, F = p * p * C;
+    float acc[C];
+#pragma unroll
+    for (int co = 0; co < C; ++co) acc[co] = __ldg(bias + co);
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+        const int yy = y + ky - 1;
+        if (yy < 0 || yy >= S) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            const int xx = x + kx - 1;
+            if (xx < 0 || xx >= S) continue;
+            const float4* row = reinterpret_cast<const float4*>(tok + (b * g * g + (yy / p) * g + xx / p) * F + ((yy % p) * p + xx % p) * C);
+            const float* wt = wsm + (ky * 3 + kx) * C * C;
+#pragma unroll
+            for (int c4 = 0; c4 < C / 4; ++c4) {
+                const float4 v = __ldg(row + c4);
+                const float in[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+#pragma unroll
+                    for (int co = 0; co < C; ++co) acc[co] = fmaf(in[q], wt[(c4 * 4 + q) * C + co], acc[co]);
+            }
+        }
+    }
+#pragma unroll
+    for (int co = 0; co < C; ++co) out[((b * C + co) * S + y) * S + x] = do_tanh ? tanhf(acc[co]) : acc[co];
+}
+void conv3x3_tokens(const float* tok, const float* w, const float* bias, float* out, int nb, int C, int S, int p, int do_tanh,
+                    cudaStream_t s) {
+    const long long total = (long long)nb * S * S;
+    const unsigned grid = (unsigned)ceil_div_ll(total, 256);
+    if (C == 4) conv3x3_tok_kernel<4><<<grid, 256, 0, s>>>(tok, w, bias, out, nb, S, p, do_tanh);
+    else if (C == 8) conv3x3_tok_kernel<8><<<grid, 256, 0, s>>>(tok, w, bias, out, nb, S, p, do_tanh);
+    else PDM_REQUIRE(false, "conv3x3_tokens: 4 or 8 channels");
+    check_launch("conv3x3_tok");
 }
 
 void head_decode(const HeadArgs& a, cudaStream_t s) {

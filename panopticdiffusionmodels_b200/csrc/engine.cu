@@ -88,6 +88,7 @@ struct Workspace {
     float *mbase = nullptr, *min_ = nullptr, *P0 = nullptr;
     float *nz = nullptr, *ny = nullptr;
     float *X1 = nullptr, *X2 = nullptr, *P1 = nullptr, *P2 = nullptr;  // 2M / 3M data-prediction history (ring with X0 / P0)
+    bf16 *pat_img = nullptr, *pat_msk = nullptr;  // [nb * P, 2 C p^2] patch rows ([hi | lo]) of the patch-embed GEMMs
 };
 
 struct GraphEntry {
@@ -111,6 +112,21 @@ struct ProfEvent {
 
 namespace pdm {
 void set_last_error(const std::string& msg) { g_last_error = msg; }
+namespace {
+__global__ void dup_weight_kernel(const float* __restrict__ w, bf16* __restrict__ out, int D, int kk) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= D * kk) return;
+    const int d = i / kk, k = i - d * kk;
+    const bf16 v = __float2bfloat16_rn(w[i]);
+    out[(size_t)d * 2 * kk + k] = v;
+    out[(size_t)d * 2 * kk + kk + k] = v;
+}
+}  // namespace
+// patch-embed weight [D, kk] fp32 -> bf16 [D, 2 kk] = [W | W] (operand of the [hi | lo] patch rows)
+void dup_weight_bf16(const float* w, bf16* out, int D, int kk, cudaStream_t s) {
+    dup_weight_kernel<<<ceil_div(D * kk, 256), 256, 0, s>>>(w, out, D, kk);
+    check_launch("dup_weight");
+}
 }  // namespace pdm
 
 using namespace pdm;
@@ -128,6 +144,10 @@ struct pdm_engine {
     LinearW ctx_lin;
     float* freqs = nullptr;
     float *wT_img = nullptr, *wT_msk = nullptr;  // patch-embed weights transposed to [C*p*p, D] (embed kernel operand)
+    // bf16 engine path: patch-embed weights as GEMM operands [D, 2 C p^2] = [W | W] (the activation rows are [hi | lo] bf16
+    // halves of the fp32 pixels), and the final LayerNorm folded into the two decoders
+    bf16 *wemb_img = nullptr, *wemb_msk = nullptr;
+    FoldW dec_img_f, dec_msk_f;
     std::vector<std::unique_ptr<Workspace>> spaces;
     std::vector<GraphEntry> graphs;
     bool profiling = false;
@@ -144,6 +164,8 @@ struct pdm_engine {
         if (freqs) cudaFree(freqs);
         if (wT_img) cudaFree(wT_img);
         if (wT_msk) cudaFree(wT_msk);
+        if (wemb_img) cudaFree(wemb_img);
+        if (wemb_msk) cudaFree(wemb_msk);
         for (auto& kv : folds) {
             if (kv.second.w) cudaFree(kv.second.w);
             if (kv.second.d) cudaFree(kv.second.d);
@@ -198,14 +220,14 @@ struct pdm_engine {
         for (int i = 0; i < depth / 2; ++i) expect_block("out_blocks." + std::to_string(i) + ".", true);
         expect("norm.weight", {d});
         expect("norm.bias", {d});
-        expect("decoder_pred.weight", {(int64_t)p * p * C, d});
+        expect("decoder_pred.weight", {(int64_t)p * p * C, d}, true);
         expect("decoder_pred.bias", {(int64_t)p * p * C});
         expect("final_layer.weight", {C, C, 3, 3});
         expect("final_layer.bias", {C});
         if (cfg.enable_panoptic) {
             expect("mask_embed.proj.weight", {d, Cm, p, p});
             expect("mask_embed.proj.bias", {d});
-            expect("decoder_pred_mask.weight", {(int64_t)p * p * Cm, d});
+            expect("decoder_pred_mask.weight", {(int64_t)p * p * Cm, d}, true);
             expect("decoder_pred_mask.bias", {(int64_t)p * p * Cm});
             expect("final_layer_mask.weight", {Cm, Cm, 3, 3});
             expect("final_layer_mask.bias", {Cm});
@@ -344,6 +366,20 @@ struct pdm_engine {
         }
         fold_block("mid_block.", mid_b, s);
         if (two) fold_block("mid_block_mask.", mid_bm, s);
+        {
+            const int kk = C * p * p;
+            if (!wemb_img) PDM_CHECK_CUDA(cudaMalloc(&wemb_img, (size_t)D * 2 * kk * sizeof(bf16)));
+            dup_weight_bf16(params.at("patch_embed.proj.weight").d32, wemb_img, D, kk, s);
+            dec_img_f = fold("decoder_pred", lin("decoder_pred.weight", "decoder_pred.bias", kk, D), params.at("norm.weight").d32,
+                             params.at("norm.bias").d32, false, s);
+            if (cfg.enable_panoptic) {
+                const int kkm = Cm * p * p;
+                if (!wemb_msk) PDM_CHECK_CUDA(cudaMalloc(&wemb_msk, (size_t)D * 2 * kkm * sizeof(bf16)));
+                dup_weight_bf16(params.at("mask_embed.proj.weight").d32, wemb_msk, D, kkm, s);
+                dec_msk_f = fold("decoder_pred_mask", lin("decoder_pred_mask.weight", "decoder_pred_mask.bias", kkm, D),
+                                 params.at("norm.weight").d32, params.at("norm.bias").d32, false, s);
+            }
+        }
         PDM_CHECK_CUDA(cudaStreamSynchronize(s));
         finalized = true;
     }
@@ -391,6 +427,8 @@ struct pdm_engine {
         w.X2 = (float*)a.take(w.nb * img * 4);
         w.P1 = (float*)a.take(w.nb * msk * 4);
         w.P2 = (float*)a.take(w.nb * msk * 4);
+        w.pat_img = w.prec == PDM_PREC_BF16 ? (bf16*)a.take((size_t)w.nb * P * 2 * C * p * p * 2) : nullptr;
+        w.pat_msk = (w.prec == PDM_PREC_BF16 && w.with_mask) ? (bf16*)a.take((size_t)w.nb * P * 2 * Cm * p * p * 2) : nullptr;
     }
     size_t workspace_bytes(int nb, int prec, bool with_mask) const {
         Workspace w;
@@ -621,9 +659,10 @@ struct pdm_engine {
                 cur = ws.skipx[i];
             }
             run_block_dln(mid_b, ws, ws.x, ws.stats_x, cur, nb, Lx, nullptr, nullptr, ws.xb, nullptr, 0, false, s);
+            // (the last block leaves the bf16 copy and the row sums of the FINAL stream: operands of the decoder GEMMs)
             for (int j = 0; j < half; ++j)
-                run_block_dln(out_b[j], ws, ws.x, ws.stats_x, nullptr, nb, Lx, ws.xb, ws.skipx[half - 1 - j],
-                              j + 1 < half ? ws.xb : nullptr, nullptr, 0, false, s);
+                run_block_dln(out_b[j], ws, ws.x, ws.stats_x, nullptr, nb, Lx, ws.xb, ws.skipx[half - 1 - j], ws.xb, nullptr, 0,
+                              j + 1 == half, s);
             return;
         }
         {
@@ -653,7 +692,9 @@ struct pdm_engine {
                           false, s);
             run_block_dln(out_bm[j], ws, ws.mx, ws.stats_mx, nullptr, nb, L2, ws.mxb, ws.skipm[half - 1 - j], ws.h,
                           more ? ws.mxb : nullptr, L1, false, s);
-            run_zero_conv_dln(zc[li], ws, ws.h, more ? ws.xb : nullptr, nb, more, false, false, s);
+            // (last layer: bf16 copy + row sums of the final image stream for the decoder GEMM; the final mask stream's bf16
+            //  copy is ws.h, left by the mask block's fc2)
+            run_zero_conv_dln(zc[li], ws, ws.h, ws.xb, nb, more, false, !more, s);
         }
     }
 
@@ -694,6 +735,8 @@ struct pdm_engine {
         const bool two_m = two && with_mask;
         const bool b16 = prec == PDM_PREC_BF16;
         const int Lx = two_m ? L1 : (with_mask ? L2 : L1);
+        static const bool dln = getenv("PDM_NO_DLN") == nullptr;  // A/B switch: the LayerNorm-kernel path of round 1a
+        const bool tc_io = b16 && dln;  // patch embed and decoders on the tcgen05 GEMM kernel
         {
             Scope sc(this, "embed", s);
             EmbedArgs a;
@@ -709,11 +752,27 @@ struct pdm_engine {
             a.out_x = ws.x; a.Lx = Lx;
             a.out_m = two_m ? ws.mx : ws.x; a.Lm = two_m ? L2 : Lx; a.m_off = ext + P;
             a.C = C; a.Cm = Cm; a.S = S; a.p = p; a.D = D; a.T = T;
-            embed_tokens(a, s);
+            if (!tc_io) {
+                embed_tokens(a, s);
+            } else {
+                // time + context tokens: copy kernel; patch tokens: [hi | lo] bf16 patch rows x [W | W]^T on the GEMM kernel,
+                // (acc + conv bias) + positional row in the epilogue, straight into the fp32 residual stream(s)
+                embed_extras(a, s);
+                auto patch_gemm = [&](const float* src, bf16* rows, int Cc, const bf16* w16, const float* bias, const float* posrows,
+                                      float* out, int out_bs) {
+                    im2col_patches(src, rows, Bx, nb, Cc, S, p, s);
+                    GemmProblem g;
+                    g.A1 = rows; g.K1 = 2 * Cc * p * p; g.W16 = w16; g.bias = bias; g.N = D;
+                    g.nb = nb; g.Lr = P; g.out32 = out; g.out32_bs = out_bs; g.rowbias = posrows;
+                    gemm_tc_bf16(g, s);
+                };
+                patch_gemm(img, ws.pat_img, C, wemb_img, a.b_img, a.pos + (size_t)ext * D, ws.x + (size_t)ext * D, Lx);
+                if (with_mask)
+                    patch_gemm(mask, ws.pat_msk, Cm, wemb_msk, a.b_msk, a.pos_m, a.out_m + (size_t)a.m_off * D, a.Lm);
+            }
         }
         const int half = depth / 2;
         const size_t actsz = b16 ? 2 : 4;
-        static const bool dln = getenv("PDM_NO_DLN") == nullptr;  // A/B switch: the LayerNorm-kernel path of round 1a
         if (b16 && dln) {
             blocks_dln(ws, nb, Lx, two_m, s);
         } else if (!two_m) {
@@ -756,21 +815,50 @@ struct pdm_engine {
         }
         {
             Scope sc(this, "head", s);
-            HeadArgs a;
-            a.x = ws.x; a.Lx = Lx; a.x_off = ext;
-            a.m = with_mask ? (two_m ? ws.mx : ws.x) : nullptr;
-            a.Lm = two_m ? L2 : Lx; a.m_off = ext + P; a.ln_m = !two_m; a.gt = gt && with_mask;
-            a.ln_w = params.at("norm.weight").d32; a.ln_b = params.at("norm.bias").d32;
-            a.w_dec = params.at("decoder_pred.weight").d32; a.b_dec = params.at("decoder_pred.bias").d32;
-            a.w_fin = params.at("final_layer.weight").d32; a.b_fin = params.at("final_layer.bias").d32;
-            a.w_decm = a.b_decm = a.w_finm = a.b_finm = nullptr;
-            if (with_mask) {
-                a.w_decm = params.at("decoder_pred_mask.weight").d32; a.b_decm = params.at("decoder_pred_mask.bias").d32;
-                a.w_finm = params.at("final_layer_mask.weight").d32; a.b_finm = params.at("final_layer_mask.bias").d32;
+            if (tc_io && !gt && C == 4 && (!with_mask || Cm == 8)) {  // (the 3x3 head kernel is instantiated for 4 / 8 channels)
+                // final LayerNorm folded into the decoders (rstd per row in the epilogue), decoder_pred / decoder_pred_mask on
+                // the GEMM kernel over the patch rows of the final stream(s) -> token-major fp32 [nb * P, p p C]; unpatchify is
+                // the gather of the 3x3 head kernel.  (Two-stream: the mask tokens are not normalised, libs/uvit_t2i.py:499-520.)
+                ln_rstd(ws.stats_x, ws.rstd, (long long)nb * Lx, D, s);
+                auto dec_gemm = [&](const void* A, int a_bs, int row0, const bf16* w16, const float* bias, const float* rstd,
+                                    int nout, float* out) {
+                    GemmProblem g;
+                    g.A1 = (const bf16*)A + (size_t)row0 * D; g.K1 = D; g.a1_bs = a_bs; g.W16 = w16; g.bias = bias; g.N = nout;
+                    g.nb = nb; g.Lr = P; g.out32 = out; g.out32_bs = P;
+                    if (rstd) {
+                        g.ln_rstd = rstd + row0; g.ln_rstd_bs = a_bs;
+                    }
+                    gemm_tc_bf16(g, s);
+                };
+                dec_gemm(ws.xb, Lx, ext, dec_img_f.w, dec_img_f.d, ws.rstd, p * p * C, ws.tmp_img);
+                conv3x3_tokens(ws.tmp_img, params.at("final_layer.weight").d32, params.at("final_layer.bias").d32, out_noise, nb, C,
+                               S, p, 0, s);
+                if (with_mask) {
+                    if (two_m)
+                        dec_gemm(ws.h, L2, ext + P, params.at("decoder_pred_mask.weight").d16,
+                                 params.at("decoder_pred_mask.bias").d32, nullptr, p * p * Cm, ws.tmp_msk);
+                    else
+                        dec_gemm(ws.xb, Lx, ext + P, dec_msk_f.w, dec_msk_f.d, ws.rstd, p * p * Cm, ws.tmp_msk);
+                    conv3x3_tokens(ws.tmp_msk, params.at("final_layer_mask.weight").d32, params.at("final_layer_mask.bias").d32,
+                                   out_mask, nb, Cm, S, p, 1, s);
+                }
+            } else {
+                HeadArgs a;
+                a.x = ws.x; a.Lx = Lx; a.x_off = ext;
+                a.m = with_mask ? (two_m ? ws.mx : ws.x) : nullptr;
+                a.Lm = two_m ? L2 : Lx; a.m_off = ext + P; a.ln_m = !two_m; a.gt = gt && with_mask;
+                a.ln_w = params.at("norm.weight").d32; a.ln_b = params.at("norm.bias").d32;
+                a.w_dec = params.at("decoder_pred.weight").d32; a.b_dec = params.at("decoder_pred.bias").d32;
+                a.w_fin = params.at("final_layer.weight").d32; a.b_fin = params.at("final_layer.bias").d32;
+                a.w_decm = a.b_decm = a.w_finm = a.b_finm = nullptr;
+                if (with_mask) {
+                    a.w_decm = params.at("decoder_pred_mask.weight").d32; a.b_decm = params.at("decoder_pred_mask.bias").d32;
+                    a.w_finm = params.at("final_layer_mask.weight").d32; a.b_finm = params.at("final_layer_mask.bias").d32;
+                }
+                a.tmp_img = ws.tmp_img; a.tmp_msk = ws.tmp_msk; a.out_img = out_noise; a.out_msk = out_mask;
+                a.nb = nb; a.C = C; a.Cm = Cm; a.S = S; a.p = p; a.D = D;
+                head_decode(a, s);
             }
-            a.tmp_img = ws.tmp_img; a.tmp_msk = ws.tmp_msk; a.out_img = out_noise; a.out_msk = out_mask;
-            a.nb = nb; a.C = C; a.Cm = Cm; a.S = S; a.p = p; a.D = D;
-            head_decode(a, s);
         }
     }
 

@@ -107,6 +107,7 @@ struct TcParams {
     // deferred LayerNorm, consumer side (bf16 form): out = rstd[row] * acc + bias[n]  (weight centred along K: no mean term)
     const float* ln_rstd;
     long long ln_bs;
+    const float* rowbias;  // plain fp32 form: [Lr, N] added per row of the batch
     // implicit-GEMM 3x3 convolution (conv_hw > 0): A through a 4-D map [C, W, H, N]
     int conv_hw, conv_W, conv_H, conv_kbc;  // pixels per image, width, height, k-blocks per tap (C / 64)
     int conv_ht, conv_wt;                   // tile = conv_ht rows x conv_wt pixels (128 consecutive output pixels)
@@ -691,12 +692,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
                             res[ps] = *reinterpret_cast<const float4*>(o32 + ps * rstep);
                     }
                 }
+                // plain form only: LayerNorm folded into the weight (out = rstd * acc + bias) and / or a per-row bias table
+                float rs[8];
+                if constexpr (EPI == EPI_F32) {
+                    if (p.ln_rstd) {
+#pragma unroll
+                        for (int ps = 0; ps < 8; ++ps) {
+                            const int t = trow0 + ps * 4 + rsub;
+                            rs[ps] = t < lr_eff ? __ldg(p.ln_rstd + (long long)b * p.ln_bs + t) : 0.f;
+                        }
+                    }
+                }
                 ptx::mbar_wait(&tfull[as], aphase);
                 ptx::tc_fence_after();
 #pragma unroll 1
                 for (int chunk = 0; chunk < NBLK; ++chunk) {
                     uint32_t v[32];
                     ptx::tmem_ld_32x32(tbase + chunk * 32, v);
+                    // per-row bias table of this chunk (L2-resident positional rows): in flight under the TMEM load / transpose
+                    float4 rbv[8];
+                    if constexpr (EPI == EPI_F32) {
+                        if (p.rowbias) {
+                            const int colr = colq + 32 * chunk;
+#pragma unroll
+                            for (int ps = 0; ps < 8; ++ps) {
+                                const int t = trow0 + ps * 4 + rsub;
+                                rbv[ps] = (colr < p.N && t < lr_eff) ? __ldg(reinterpret_cast<const float4*>(p.rowbias + (long long)t * p.N + colr))
+                                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+                            }
+                        }
+                    }
                     ptx::tmem_ld_wait();
                     if (chunk == NBLK - 1) release_accumulator<NCTA>(&tempty[as], rank, lane);
                     uint32_t* srow = scr + lane * SCR_STRIDE;
@@ -718,7 +743,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
                         const int r = ps * 4 + rsub;
                         const bool row_ok = trow0 + r < lr_eff;
                         float4 a = *reinterpret_cast<const float4*>(scr + r * SCR_STRIDE + c8 * 4);
+                        if constexpr (EPI == EPI_F32) {
+                            if (p.ln_rstd) { a.x *= rs[ps]; a.y *= rs[ps]; a.z *= rs[ps]; a.w *= rs[ps]; }
+                        }
                         a.x += bb.x; a.y += bb.y; a.z += bb.z; a.w += bb.w;
+                        if constexpr (EPI == EPI_F32) {
+                            if (p.rowbias) { a.x += rbv[ps].x; a.y += rbv[ps].y; a.z += rbv[ps].z; a.w += rbv[ps].w; }
+                        }
                         if (p.gelu) {
                             a.x = gelu_fast(a.x); a.y = gelu_fast(a.y); a.z = gelu_fast(a.z); a.w = gelu_fast(a.w);
                         }
@@ -843,6 +874,7 @@ void launch(const GemmProblem& g, cudaStream_t s) {
     p.npart = ceil_div(g.N, LN_PART);
     p.ln_rstd = g.ln_rstd;
     p.ln_bs = g.ln_rstd_bs ? g.ln_rstd_bs : g.Lr;
+    p.rowbias = g.rowbias;
     p.conv_hw = p.conv_W = p.conv_H = p.conv_kbc = p.conv_ht = p.conv_wt = 0;
     if (g.conv_H > 0) {
         p.conv_hw = g.conv_H * g.conv_W;
@@ -967,8 +999,10 @@ void gemm_tc_bf16(const GemmProblem& g, cudaStream_t s) {
     PDM_REQUIRE(!g.out32b || g.out32, "gemm_tc: out32b needs out32");
     PDM_REQUIRE(!g.resid || (g.resid == g.out32 && (g.resid_bs ? g.resid_bs : g.Lr) == (g.out32_bs ? g.out32_bs : g.Lr)),
                 "gemm_tc: the residual must be the fp32 output (in-place accumulate)");
-    PDM_REQUIRE(!g.ln_rstd || (g.bias && !g.A2 && !g.out32 && g.N % 8 == 0),
-                "gemm_tc: the LayerNorm-consuming form needs the folded bias, a single A and a bf16-only output");
+    PDM_REQUIRE(!g.ln_rstd || (g.bias && !g.A2 && (g.out32 ? (!g.resid && !g.stats && !g.out2 && !g.out2b && !g.gelu) : g.N % 8 == 0)),
+                "gemm_tc: the LayerNorm-consuming form needs the folded bias, a single A and a bf16-only (or plain fp32) output");
+    PDM_REQUIRE(!g.rowbias || (g.out32 && !g.resid && !g.stats && !g.out2 && !g.out2b && !g.gelu),
+                "gemm_tc: rowbias belongs to the plain fp32-output form");
     PDM_REQUIRE(g.out32 || g.N % 8 == 0, "gemm_tc: the bf16-only output form needs N % 8 == 0");
     PDM_REQUIRE((!g.stats && !g.statsb && !g.out2b) || g.out32, "gemm_tc: row sums / out2b belong to the fp32-output form");
     PDM_REQUIRE(!g.statsb || g.stats, "gemm_tc: statsb needs stats");

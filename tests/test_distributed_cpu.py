@@ -62,3 +62,16 @@ def test_single_process_passthrough():
     from panopticdiffusionmodels_b200 import distributed as D
     z, pm = D.sample_all(lambda b: (torch.ones(b, 4, 2, 2), None), n_samples=5, mini_batch_size=2)
     assert z.shape == (5, 4, 2, 2) and pm is None
+
+
+def test_context_indices_follow_the_gather_order():
+    """sample_t2i draws captions in contiguous per-rank blocks inside each global batch, so the rank-major all-gather puts the
+    sample of caption i at output index i (the reference gathers the same way, utils.py:585-588)."""
+    from panopticdiffusionmodels_b200.sample_t2i import context_indices
+    mbs, n = 3, 2
+    order = []
+    for batch in range(2):                       # global batches, gathered rank-major
+        for rank in range(n):
+            order += context_indices(batch, mbs, rank, n, total=100)
+    assert order == list(range(2 * mbs * n))
+    assert context_indices(0, 4, 1, 2, total=6) == [4, 5, 0, 1]     # wraps around a short caption list
