@@ -115,6 +115,10 @@ struct GemmProblem {
     // (gamma * W, centred along K) and `bias` holds bias + W.beta, so that out = rstd * acc + bias == LN(x).W^T + b
     const float* ln_rstd = nullptr;  // [rows] 1 / sqrt(var + eps) of x, from ln_rstd() over the producer's row sums
     int ln_rstd_bs = 0;
+    // ... or the producer's partial row sums themselves: [rows][ceil(ln_D / 128)][2]; the epilogue then forms
+    // 1 / sqrt(E[x^2] - E[x]^2 + 1e-5) itself (same arithmetic as ln_rstd(): no separate kernel between the GEMMs)
+    const float* ln_stats = nullptr;
+    int ln_stats_bs = 0, ln_D = 0;
     // plain fp32-output form only (no residual, no copies): ln_rstd is honoured there too (out = rstd * acc + bias), and
     // rowbias [Lr, N] (fp32) is added per ROW OF THE BATCH after the bias (positional embedding of the patch-embed GEMM)
     const float* rowbias = nullptr;

@@ -583,8 +583,7 @@ struct pdm_engine {
         {
             Scope sc(this, "gemm_qkv", s);
             GemmProblem g;
-            ln_rstd(stats, ws.rstd, R, D, s);
-            g.A1 = cur; g.K1 = D; g.W16 = w.qkv_f.w; g.bias = w.qkv_f.d; g.ln_rstd = ws.rstd;
+            g.A1 = cur; g.K1 = D; g.W16 = w.qkv_f.w; g.bias = w.qkv_f.d; g.ln_stats = stats; g.ln_D = D;
             g.N = 3 * D; g.nb = 1; g.Lr = R; g.out2 = ws.qkv;
             gemm_tc_bf16(g, s);
         }
@@ -602,8 +601,7 @@ struct pdm_engine {
         {
             Scope sc(this, "gemm_fc1", s);
             GemmProblem g;
-            ln_rstd(stats, ws.rstd, R, D, s);
-            g.A1 = ws.h; g.K1 = D; g.W16 = w.fc1_f.w; g.bias = w.fc1_f.d; g.ln_rstd = ws.rstd;
+            g.A1 = ws.h; g.K1 = D; g.W16 = w.fc1_f.w; g.bias = w.fc1_f.d; g.ln_stats = stats; g.ln_D = D;
             g.N = w.fc1.N; g.nb = 1; g.Lr = R; g.out2 = ws.u; g.gelu = true;
             gemm_tc_bf16(g, s);
         }
@@ -819,18 +817,18 @@ struct pdm_engine {
                 // final LayerNorm folded into the decoders (rstd per row in the epilogue), decoder_pred / decoder_pred_mask on
                 // the GEMM kernel over the patch rows of the final stream(s) -> token-major fp32 [nb * P, p p C]; unpatchify is
                 // the gather of the 3x3 head kernel.  (Two-stream: the mask tokens are not normalised, libs/uvit_t2i.py:499-520.)
-                ln_rstd(ws.stats_x, ws.rstd, (long long)nb * Lx, D, s);
-                auto dec_gemm = [&](const void* A, int a_bs, int row0, const bf16* w16, const float* bias, const float* rstd,
+                const int npart = (D + LN_PART - 1) / LN_PART;
+                auto dec_gemm = [&](const void* A, int a_bs, int row0, const bf16* w16, const float* bias, const float* stats,
                                     int nout, float* out) {
                     GemmProblem g;
                     g.A1 = (const bf16*)A + (size_t)row0 * D; g.K1 = D; g.a1_bs = a_bs; g.W16 = w16; g.bias = bias; g.N = nout;
                     g.nb = nb; g.Lr = P; g.out32 = out; g.out32_bs = P;
-                    if (rstd) {
-                        g.ln_rstd = rstd + row0; g.ln_rstd_bs = a_bs;
+                    if (stats) {
+                        g.ln_stats = stats + (size_t)row0 * npart * 2; g.ln_stats_bs = a_bs; g.ln_D = D;
                     }
                     gemm_tc_bf16(g, s);
                 };
-                dec_gemm(ws.xb, Lx, ext, dec_img_f.w, dec_img_f.d, ws.rstd, p * p * C, ws.tmp_img);
+                dec_gemm(ws.xb, Lx, ext, dec_img_f.w, dec_img_f.d, ws.stats_x, p * p * C, ws.tmp_img);
                 conv3x3_tokens(ws.tmp_img, params.at("final_layer.weight").d32, params.at("final_layer.bias").d32, out_noise, nb, C,
                                S, p, 0, s);
                 if (with_mask) {
@@ -838,7 +836,7 @@ struct pdm_engine {
                         dec_gemm(ws.h, L2, ext + P, params.at("decoder_pred_mask.weight").d16,
                                  params.at("decoder_pred_mask.bias").d32, nullptr, p * p * Cm, ws.tmp_msk);
                     else
-                        dec_gemm(ws.xb, Lx, ext + P, dec_msk_f.w, dec_msk_f.d, ws.rstd, p * p * Cm, ws.tmp_msk);
+                        dec_gemm(ws.xb, Lx, ext + P, dec_msk_f.w, dec_msk_f.d, ws.stats_x, p * p * Cm, ws.tmp_msk);
                     conv3x3_tokens(ws.tmp_msk, params.at("final_layer_mask.weight").d32, params.at("final_layer_mask.bias").d32,
                                    out_mask, nb, Cm, S, p, 1, s);
                 }
@@ -1327,8 +1325,7 @@ int pdm_debug_ln_chain(const float* A, const float* W1, const float* b1, const f
         fold_ln_weight(W2, b2, gamma, beta, (bf16*)wf.p, (float*)d.p, N, D, gelu != 0, s);
         GemmProblem g;
         g.A1 = xb.p; g.K1 = D; g.W16 = (const bf16*)wf.p; g.bias = (const float*)d.p;
-        ln_rstd((const float*)stats.p, (float*)rs.p, M, D, s);
-        g.ln_rstd = (const float*)rs.p; g.N = N; g.nb = 1; g.Lr = M; g.out2 = o16.p; g.gelu = gelu != 0;
+        g.ln_stats = (const float*)stats.p; g.ln_D = D; g.N = N; g.nb = 1; g.Lr = M; g.out2 = o16.p; g.gelu = gelu != 0;
         gemm_tc_bf16(g, s);
         time_kernel([&] { gemm_tc_bf16(g, s); }, iters, ms, s);
         bf16_to_f32_kernel<<<(unsigned)ceil_div_ll((long long)M * N, 256), 256, 0, s>>>((const bf16*)o16.p, out,

@@ -107,6 +107,9 @@ struct TcParams {
     // deferred LayerNorm, consumer side (bf16 form): out = rstd[row] * acc + bias[n]  (weight centred along K: no mean term)
     const float* ln_rstd;
     long long ln_bs;
+    const float* ln_stats;  // alternative to ln_rstd: partial row sums [rows][ln_npart][2] -> rstd formed in the epilogue
+    int ln_npart;
+    float ln_invD;
     const float* rowbias;  // plain fp32 form: [Lr, N] added per row of the batch
     // implicit-GEMM 3x3 convolution (conv_hw > 0): A through a 4-D map [C, W, H, N]
     int conv_hw, conv_W, conv_H, conv_kbc;  // pixels per image, width, height, k-blocks per tap (C / 64)
@@ -200,6 +203,23 @@ __device__ __forceinline__ void gelu_fast2_half(float& h0, float& h1) {
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// 1 / std of row (b, t) for the LayerNorm-folded forms: a precomputed value, or formed here from the producer's partial row
+// sums with the arithmetic of ln_rstd_kernel (elementwise.cu): mean = S1 / D, var = max(S2 / D - mean^2, 0), rsqrt(var + 1e-5)
+__device__ __forceinline__ float row_rstd(const TcParams& p, long long b, int t) {
+    if (p.ln_stats) {
+        const float2* st = reinterpret_cast<const float2*>(p.ln_stats) + (b * p.ln_bs + t) * p.ln_npart;
+        float a1 = 0.f, a2 = 0.f;
+        for (int i = 0; i < p.ln_npart; ++i) {
+            const float2 v = __ldg(st + i);
+            a1 += v.x;
+            a2 += v.y;
+        }
+        const float mean = a1 * p.ln_invD;
+        return rsqrtf(fmaxf(fmaf(-mean, mean, a2 * p.ln_invD), 0.f) + 1e-5f);
+    }
+    return __ldg(p.ln_rstd + b * p.ln_bs + t);
 }
 
 template <int NCTA>
@@ -412,7 +432,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
                 if (mt < p.n_mtiles) {
                     const int b = mt / p.tpb;
                     const int t = (mt - b * p.tpb) * BM + q * 32 + lane;
-                    if (t < p.Lr) r = __ldg(p.ln_rstd + (long long)b * p.ln_bs + t);
+                    if (t < p.Lr) r = row_rstd(p, b, t);
                 }
             }
             return r;
@@ -699,7 +719,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
 #pragma unroll
                         for (int ps = 0; ps < 8; ++ps) {
                             const int t = trow0 + ps * 4 + rsub;
-                            rs[ps] = t < lr_eff ? __ldg(p.ln_rstd + (long long)b * p.ln_bs + t) : 0.f;
+                            rs[ps] = t < lr_eff ? row_rstd(p, b, t) : 0.f;
                         }
                     }
                 }
@@ -874,6 +894,15 @@ void launch(const GemmProblem& g, cudaStream_t s) {
     p.npart = ceil_div(g.N, LN_PART);
     p.ln_rstd = g.ln_rstd;
     p.ln_bs = g.ln_rstd_bs ? g.ln_rstd_bs : g.Lr;
+    p.ln_stats = g.ln_stats;
+    p.ln_npart = 0;
+    p.ln_invD = 0.f;
+    if (g.ln_stats) {
+        p.ln_rstd = g.ln_stats;  // non-null marker for the forms that test ln_rstd
+        p.ln_bs = g.ln_stats_bs ? g.ln_stats_bs : g.Lr;
+        p.ln_npart = ceil_div(g.ln_D, LN_PART);
+        p.ln_invD = 1.f / (float)g.ln_D;
+    }
     p.rowbias = g.rowbias;
     p.conv_hw = p.conv_W = p.conv_H = p.conv_kbc = p.conv_ht = p.conv_wt = 0;
     if (g.conv_H > 0) {
@@ -999,7 +1028,9 @@ void gemm_tc_bf16(const GemmProblem& g, cudaStream_t s) {
     PDM_REQUIRE(!g.out32b || g.out32, "gemm_tc: out32b needs out32");
     PDM_REQUIRE(!g.resid || (g.resid == g.out32 && (g.resid_bs ? g.resid_bs : g.Lr) == (g.out32_bs ? g.out32_bs : g.Lr)),
                 "gemm_tc: the residual must be the fp32 output (in-place accumulate)");
-    PDM_REQUIRE(!g.ln_rstd || (g.bias && !g.A2 && (g.out32 ? (!g.resid && !g.stats && !g.out2 && !g.out2b && !g.gelu) : g.N % 8 == 0)),
+    PDM_REQUIRE(!(g.ln_rstd && g.ln_stats) && (!g.ln_stats || g.ln_D > 0), "gemm_tc: ln_rstd or ln_stats (+ ln_D), not both");
+    const bool ln = g.ln_rstd || g.ln_stats;
+    PDM_REQUIRE(!ln || (g.bias && !g.A2 && (g.out32 ? (!g.resid && !g.stats && !g.out2 && !g.out2b && !g.gelu) : g.N % 8 == 0)),
                 "gemm_tc: the LayerNorm-consuming form needs the folded bias, a single A and a bf16-only (or plain fp32) output");
     PDM_REQUIRE(!g.rowbias || (g.out32 && !g.resid && !g.stats && !g.out2 && !g.out2b && !g.gelu),
                 "gemm_tc: rowbias belongs to the plain fp32-output form");
@@ -1022,7 +1053,7 @@ void gemm_tc_bf16(const GemmProblem& g, cudaStream_t s) {
     const bool tma_ok = tma_epi && g.out32 && (g.resid || tma_noresid) && !g.gelu && g.N % 32 == 0 && K_total(g) <= tma_maxk &&
                         (!g.out2b || (g.out2b_row0 == 0 && g.out2b_mod == 0));
     const int epi = g.out32 ? (tma_ok ? EPI_F32_TMA : ((g.stats || g.out2b) ? EPI_F32_EMIT : EPI_F32))
-                            : (g.ln_rstd ? (g.gelu ? (g.K1 <= 512 ? EPI_LN_GELU_W16 : EPI_LN_GELU) : EPI_LN) : EPI_PACK);
+                            : (ln ? (g.gelu ? (g.K1 <= 512 ? EPI_LN_GELU_W16 : EPI_LN_GELU) : EPI_LN) : EPI_PACK);
     if (one_cta) {
         if (epi == EPI_F32) launch<1, EPI_F32>(g, s);
         else if (epi == EPI_F32_TMA) launch<1, EPI_F32_TMA>(g, s);
