@@ -170,6 +170,14 @@ struct EmbedArgs {
     float* out_m;          // [nb, Lm, D] mask tokens written at token offset m_off
     int Lm, m_off;
     int C, Cm, S, p, D, T;
+    // bf16 engine path (embed_extras): the time / context rows also leave their bf16 copy and LayerNorm row sums, and (two-stream)
+    // the same three things in the mask stream's buffers -- the concat of libs/uvit_t2i.py:427 and the first row-statistics pass
+    bf16* xb = nullptr;        // [nb, Lx, D]
+    float* stats = nullptr;    // [nb, Lx, ceil(D / 128), 2]
+    float* out_x2 = nullptr;   // [nb, L2rows, D] (null: no mirror)
+    bf16* xb2 = nullptr;
+    float* stats2 = nullptr;
+    int L2rows = 0;
 };
 void embed_tokens(const EmbedArgs& a, cudaStream_t s);
 void transpose_f32(const float* in, float* out, int R, int C, cudaStream_t s);  // [R, C] -> [C, R]

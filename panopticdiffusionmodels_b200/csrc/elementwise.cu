@@ -404,8 +404,66 @@ void im2col_patches(const float* img, bf16* out, int Bx, int nb, int C, int S, i
     im2col_patch_kernel<<<grid, 256, 0, s>>>(img, out, Bx, nb, C, S, p);
     check_launch("im2col_patches");
 }
+// time + context tokens of the bf16 engine path: fp32 row, its bf16 copy and the per-128-column partial row sums (the
+// deferred-LayerNorm producer contract of the GEMM epilogues), optionally mirrored into the mask stream's buffers (two-stream
+// concat).  128 threads = 4 warps; warp w owns the 128-column slices w, w + 4, ... of the row.
+__global__ void __launch_bounds__(128) embed_extras_emit_kernel(EmbedArgs a) {
+    const int tok = blockIdx.x;  // 0 .. T
+    const int b = blockIdx.y;
+    const int bi = b % a.Bx;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int npart = (a.D + LN_PART - 1) / LN_PART;
+    const long long r1 = (long long)b * a.Lx + tok, r2 = (long long)b * a.L2rows + tok;
+    const float* pe = a.pos + (long long)tok * a.D;
+    const float t = tok == 0 ? (a.t_dev ? a.t_dev[bi] : a.t_scalar) : 0.f;
+    const int half = a.D / 2;
+    for (int part = warp; part < npart; part += 4) {
+        const int d = part * LN_PART + lane * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (d < a.D) {
+            const float4 q = __ldg(reinterpret_cast<const float4*>(pe + d));
+            if (tok == 0) {
+                float e[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int dd = d + k;
+                    float u = 0.f;
+                    if (dd < 2 * half) {
+                        const float arg = t * a.freqs[dd < half ? dd : dd - half];
+                        u = dd < half ? cosf(arg) : sinf(arg);
+                    }
+                    e[k] = u;
+                }
+                v = make_float4(e[0] + q.x, e[1] + q.y, e[2] + q.z, e[3] + q.w);
+            } else {
+                const float4 u = __ldg(reinterpret_cast<const float4*>(a.ctxtok + ((long long)b * a.T + (tok - 1)) * a.D + d));
+                v = make_float4(u.x + q.x, u.y + q.y, u.z + q.z, u.w + q.w);
+            }
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+            const uint2 hb = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+            *reinterpret_cast<float4*>(a.out_x + r1 * a.D + d) = v;
+            *reinterpret_cast<uint2*>(a.xb + r1 * a.D + d) = hb;
+            if (a.out_x2) {
+                *reinterpret_cast<float4*>(a.out_x2 + r2 * a.D + d) = v;
+                *reinterpret_cast<uint2*>(a.xb2 + r2 * a.D + d) = hb;
+            }
+        }
+        float s1 = (v.x + v.y) + (v.z + v.w);
+        float s2 = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, v.w * v.w)));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        }
+        if (lane == 0) {
+            reinterpret_cast<float2*>(a.stats)[r1 * npart + part] = make_float2(s1, s2);
+            if (a.stats2) reinterpret_cast<float2*>(a.stats2)[r2 * npart + part] = make_float2(s1, s2);
+        }
+    }
+}
 void embed_extras(const EmbedArgs& a, cudaStream_t s) {
-    embed_extras_kernel<<<dim3(1 + a.T, a.nb), 128, 0, s>>>(a);
+    PDM_REQUIRE(a.xb && a.stats && a.D % 4 == 0, "embed_extras: bf16 copy / row-sum destinations missing");
+    embed_extras_emit_kernel<<<dim3(1 + a.T, a.nb), 128, 0, s>>>(a);
     check_launch("embed_extras");
 }
 

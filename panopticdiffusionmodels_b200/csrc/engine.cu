@@ -646,10 +646,8 @@ struct pdm_engine {
 
     void blocks_dln(Workspace& ws, int nb, int Lx, bool two_m, cudaStream_t s) {
         const int half = depth / 2;
-        {
-            Scope sc(this, "layernorm", s);  // the only remaining row-statistics pass: the embed output
-            rowstats_convert(ws.x, (bf16*)ws.xb, ws.stats_x, (long long)nb * Lx, D, s);
-        }
+        // (the embed -- embed_extras + the patch-embed GEMM epilogues -- has left the bf16 copies ws.xb / ws.mxb, the row sums
+        //  stats_x / stats_mx and, two-stream, the image rows of mx: no row-statistics pass and no concat copy run here)
         if (!two_m) {
             const void* cur = ws.xb;
             for (int i = 0; i < half; ++i) {
@@ -662,14 +660,6 @@ struct pdm_engine {
                 run_block_dln(out_b[j], ws, ws.x, ws.stats_x, nullptr, nb, Lx, ws.xb, ws.skipx[half - 1 - j], ws.xb, nullptr, 0,
                               j + 1 == half, s);
             return;
-        }
-        {
-            Scope sc(this, "concat", s);  // mx[:, :L1] = x: the only concat that runs as a kernel
-            copy_rows(ws.mx, L2, ws.x, L1, L1, nb, D * 4, s);
-        }
-        {
-            Scope sc(this, "layernorm", s);
-            rowstats_convert(ws.mx, (bf16*)ws.mxb, ws.stats_mx, (long long)nb * L2, D, s);
         }
         const void* cur_x = ws.xb;
         int li = 0;
@@ -754,19 +744,39 @@ struct pdm_engine {
                 embed_tokens(a, s);
             } else {
                 // time + context tokens: copy kernel; patch tokens: [hi | lo] bf16 patch rows x [W | W]^T on the GEMM kernel,
-                // (acc + conv bias) + positional row in the epilogue, straight into the fp32 residual stream(s)
+                // (acc + conv bias) + positional row in the epilogue, straight into the fp32 residual stream(s).  Both also
+                // leave the bf16 copy and the LayerNorm row sums of what they write, and (two-stream) mirror the image stream's
+                // rows into the mask stream's buffers: the first row-statistics pass and the concat of libs/uvit_t2i.py:427
+                // never run as kernels.
+                const int npart = (D + LN_PART - 1) / LN_PART;
+                a.xb = (bf16*)ws.xb; a.stats = ws.stats_x;
+                if (two_m) {
+                    a.out_x2 = ws.mx; a.xb2 = (bf16*)ws.mxb; a.stats2 = ws.stats_mx; a.L2rows = L2;
+                }
                 embed_extras(a, s);
+                struct Dst {
+                    float* x; bf16* xb; float* stats; int bs;
+                };
                 auto patch_gemm = [&](const float* src, bf16* rows, int Cc, const bf16* w16, const float* bias, const float* posrows,
-                                      float* out, int out_bs) {
+                                      int row0, Dst d, const Dst* mirror) {
                     im2col_patches(src, rows, Bx, nb, Cc, S, p, s);
                     GemmProblem g;
                     g.A1 = rows; g.K1 = 2 * Cc * p * p; g.W16 = w16; g.bias = bias; g.N = D;
-                    g.nb = nb; g.Lr = P; g.out32 = out; g.out32_bs = out_bs; g.rowbias = posrows;
+                    g.nb = nb; g.Lr = P; g.rowbias = posrows;
+                    g.out32 = d.x + (size_t)row0 * D; g.out32_bs = d.bs;
+                    g.out2 = d.xb + (size_t)row0 * D; g.out2_bs = d.bs;
+                    g.stats = d.stats + (size_t)row0 * npart * 2; g.stats_bs = d.bs;
+                    if (mirror) {
+                        g.out32b = mirror->x + (size_t)row0 * D; g.out32b_bs = mirror->bs;
+                        g.out2b = mirror->xb + (size_t)row0 * D; g.out2b_bs = mirror->bs;
+                        g.statsb = mirror->stats + (size_t)row0 * npart * 2; g.statsb_bs = mirror->bs;
+                    }
                     gemm_tc_bf16(g, s);
                 };
-                patch_gemm(img, ws.pat_img, C, wemb_img, a.b_img, a.pos + (size_t)ext * D, ws.x + (size_t)ext * D, Lx);
-                if (with_mask)
-                    patch_gemm(mask, ws.pat_msk, Cm, wemb_msk, a.b_msk, a.pos_m, a.out_m + (size_t)a.m_off * D, a.Lm);
+                const Dst dx{ws.x, (bf16*)ws.xb, ws.stats_x, Lx};
+                const Dst dm{ws.mx, (bf16*)ws.mxb, ws.stats_mx, L2};
+                patch_gemm(img, ws.pat_img, C, wemb_img, a.b_img, a.pos + (size_t)ext * D, ext, dx, two_m ? &dm : nullptr);
+                if (with_mask) patch_gemm(mask, ws.pat_msk, Cm, wemb_msk, a.b_msk, a.pos_m, ext + P, two_m ? dm : dx, nullptr);
             }
         }
         const int half = depth / 2;

@@ -45,7 +45,8 @@ constexpr int BN = 256, BK = 64;
 #endif
 constexpr int A_BYTES = BM * BK * 2;
 constexpr int SCR_STRIDE = 36;  // 32-bit words per scratch row: 128 B payload + 16 B pad (16 B aligned, conflict-free)
-enum { EPI_F32 = 0, EPI_PACK = 1, EPI_LN = 2, EPI_LN_GELU = 3, EPI_F32_EMIT = 4, EPI_LN_GELU_W16 = 5, EPI_F32_TMA = 6 };
+enum { EPI_F32 = 0, EPI_PACK = 1, EPI_LN = 2, EPI_LN_GELU = 3, EPI_F32_EMIT = 4, EPI_LN_GELU_W16 = 5, EPI_F32_TMA = 6,
+       EPI_F32_EMIT_RB = 7 };  // _RB: EMIT + per-row bias table (the patch-embed GEMM: positional rows, bf16 copies, row sums)
 constexpr int TMA_WARP_BYTES = 3 * 4096 + 2048;  // EPI_F32_TMA: 3 fp32 [32 x 32] staging tiles + 1 bf16 [32 x 32] tile per warp
 
 // Epilogue geometry per form.  Each epilogue warp covers one TMEM lane quarter x WCOLS accumulator columns.  The
@@ -419,8 +420,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         const int half = ew >> 2;  // which WCOLS-column slice of the tile
         uint32_t* scr = reinterpret_cast<uint32_t*>(scr_base + ew * SCR_BYTES);
         float* sbias = reinterpret_cast<float*>(scr + (G::TMA ? TMA_WARP_BYTES / 4 : (G::PTMA ? 1024 : 32 * SCR_STRIDE)));  // [WCOLS]
-        constexpr bool packed = EPI != EPI_F32 && EPI != EPI_F32_EMIT && EPI != EPI_F32_TMA;
-        constexpr bool EMIT = EPI == EPI_F32_EMIT;
+        constexpr bool packed = EPI != EPI_F32 && EPI != EPI_F32_EMIT && EPI != EPI_F32_TMA && EPI != EPI_F32_EMIT_RB;
+        constexpr bool EMIT = EPI == EPI_F32_EMIT || EPI == EPI_F32_EMIT_RB;
+        constexpr bool RB = EPI == EPI_F32 || EPI == EPI_F32_EMIT_RB;  // forms that honour p.rowbias
         constexpr bool LN = G::LN;
         // deferred LayerNorm: 1 / std of the accumulator row this thread owns, fetched ONE TILE AHEAD into a register (read
         // at the top of a tile it cost an L2 / HBM round trip during which the finished accumulator sat unread)
@@ -731,7 +733,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
                     ptx::tmem_ld_32x32(tbase + chunk * 32, v);
                     // per-row bias table of this chunk (L2-resident positional rows): in flight under the TMEM load / transpose
                     float4 rbv[8];
-                    if constexpr (EPI == EPI_F32) {
+                    if constexpr (RB) {
                         if (p.rowbias) {
                             const int colr = colq + 32 * chunk;
 #pragma unroll
@@ -767,7 +769,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
                             if (p.ln_rstd) { a.x *= rs[ps]; a.y *= rs[ps]; a.z *= rs[ps]; a.w *= rs[ps]; }
                         }
                         a.x += bb.x; a.y += bb.y; a.z += bb.z; a.w += bb.w;
-                        if constexpr (EPI == EPI_F32) {
+                        if constexpr (RB) {
                             if (p.rowbias) { a.x += rbv[ps].x; a.y += rbv[ps].y; a.z += rbv[ps].z; a.w += rbv[ps].w; }
                         }
                         if (p.gelu) {
@@ -1032,8 +1034,7 @@ void gemm_tc_bf16(const GemmProblem& g, cudaStream_t s) {
     const bool ln = g.ln_rstd || g.ln_stats;
     PDM_REQUIRE(!ln || (g.bias && !g.A2 && (g.out32 ? (!g.resid && !g.stats && !g.out2 && !g.out2b && !g.gelu) : g.N % 8 == 0)),
                 "gemm_tc: the LayerNorm-consuming form needs the folded bias, a single A and a bf16-only (or plain fp32) output");
-    PDM_REQUIRE(!g.rowbias || (g.out32 && !g.resid && !g.stats && !g.out2 && !g.out2b && !g.gelu),
-                "gemm_tc: rowbias belongs to the plain fp32-output form");
+    PDM_REQUIRE(!g.rowbias || (g.out32 && !g.resid && !g.gelu), "gemm_tc: rowbias belongs to the fp32-output forms without residual");
     PDM_REQUIRE(g.out32 || g.N % 8 == 0, "gemm_tc: the bf16-only output form needs N % 8 == 0");
     PDM_REQUIRE((!g.stats && !g.statsb && !g.out2b) || g.out32, "gemm_tc: row sums / out2b belong to the fp32-output form");
     PDM_REQUIRE(!g.statsb || g.stats, "gemm_tc: statsb needs stats");
@@ -1052,12 +1053,13 @@ void gemm_tc_bf16(const GemmProblem& g, cudaStream_t s) {
     static const bool tma_noresid = getenv("PDM_GEMM_TMA_NORESID") != nullptr;
     const bool tma_ok = tma_epi && g.out32 && (g.resid || tma_noresid) && !g.gelu && g.N % 32 == 0 && K_total(g) <= tma_maxk &&
                         (!g.out2b || (g.out2b_row0 == 0 && g.out2b_mod == 0));
-    const int epi = g.out32 ? (tma_ok ? EPI_F32_TMA : ((g.stats || g.out2b) ? EPI_F32_EMIT : EPI_F32))
+    const int epi = g.out32 ? (tma_ok ? EPI_F32_TMA : ((g.stats || g.out2b) ? (g.rowbias ? EPI_F32_EMIT_RB : EPI_F32_EMIT) : EPI_F32))
                             : (ln ? (g.gelu ? (g.K1 <= 512 ? EPI_LN_GELU_W16 : EPI_LN_GELU) : EPI_LN) : EPI_PACK);
     if (one_cta) {
         if (epi == EPI_F32) launch<1, EPI_F32>(g, s);
         else if (epi == EPI_F32_TMA) launch<1, EPI_F32_TMA>(g, s);
         else if (epi == EPI_F32_EMIT) launch<1, EPI_F32_EMIT>(g, s);
+        else if (epi == EPI_F32_EMIT_RB) launch<1, EPI_F32_EMIT_RB>(g, s);
         else if (epi == EPI_PACK) launch<1, EPI_PACK>(g, s);
         else if (epi == EPI_LN) launch<1, EPI_LN>(g, s);
         else if (epi == EPI_LN_GELU_W16) launch<1, EPI_LN_GELU_W16>(g, s);
@@ -1066,6 +1068,7 @@ void gemm_tc_bf16(const GemmProblem& g, cudaStream_t s) {
         if (epi == EPI_F32) launch<2, EPI_F32>(g, s);
         else if (epi == EPI_F32_TMA) launch<2, EPI_F32_TMA>(g, s);
         else if (epi == EPI_F32_EMIT) launch<2, EPI_F32_EMIT>(g, s);
+        else if (epi == EPI_F32_EMIT_RB) launch<2, EPI_F32_EMIT_RB>(g, s);
         else if (epi == EPI_PACK) launch<2, EPI_PACK>(g, s);
         else if (epi == EPI_LN) launch<2, EPI_LN>(g, s);
         else if (epi == EPI_LN_GELU_W16) launch<2, EPI_LN_GELU_W16>(g, s);
