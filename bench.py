@@ -10,7 +10,7 @@ CFG/solver updates), VAE / CLIP excluded (they run once per sample outside the l
   torchrun --nproc-per-node N bench.py --gpus N ...              # weak scaling: batch per GPU fixed
 
 One JSON line on stdout (rank 0).  `value` is BASELINE config 2 (mscoco_uvit_small as shipped, batch 256 per GPU); the
-`configs` object of the same line carries short runs (2 warm-ups + 3 timed steps) of the other BASELINE configs --
+`configs` object of the same line carries short runs (3 warm-ups + 3 timed steps) of the other BASELINE configs --
 large (U-ViT-L/2, batch 128 per GPU: the north-star headline), mid (global batch 512 sharded over the GPUs: strong scaling)
 and small_512 (batch 32 per GPU, attention-bound) -- each with its own samples/s, roofline (GEMM and attention) and clocks.
 Baselines beside it, all outside the timed regions: `cpu_baseline` (oracle port on the host cores, rank 0, N = 1) and
@@ -441,7 +441,7 @@ def run_ours(a):
     if a.config is None and not a.no_extra_configs and a.method == "fast" and not a.batch:
         for name, scaling in (("large", "weak"), ("mid", "strong"), ("small_512", "weak")):
             Bx = default_batch(name, a.gpus) if name != "mid" else max(64, 512 // world)
-            r, _ = measure(a, name, Bx, 3, 2, rank, world, dev, with_e2e=False, with_profile=not a.no_kernel_profile,
+            r, _ = measure(a, name, Bx, 3, 3, rank, world, dev, with_e2e=False, with_profile=not a.no_kernel_profile,
                            scaling=scaling)
             r.pop("kernels", None)
             extra[name] = {"samples_per_s": r.pop("value"), "unit": "samples/s", "global_batch": Bx * world, **r}

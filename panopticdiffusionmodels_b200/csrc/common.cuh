@@ -113,10 +113,10 @@ struct GemmProblem {
     int statsb_bs = 0;
     // consumer side (bf16-output form): A1 holds the RAW rows bf16(x); W16 holds the LN-folded weight of fold_ln_weight
     // (gamma * W, centred along K) and `bias` holds bias + W.beta, so that out = rstd * acc + bias == LN(x).W^T + b
-    const float* ln_rstd = nullptr;  // [rows] 1 / sqrt(var + eps) of x, from ln_rstd() over the producer's row sums
+    const float* ln_rstd = nullptr;  // [rows] 1 / sqrt(var + eps) of x, precomputed by the caller
     int ln_rstd_bs = 0;
     // ... or the producer's partial row sums themselves: [rows][ceil(ln_D / 128)][2]; the epilogue then forms
-    // 1 / sqrt(E[x^2] - E[x]^2 + 1e-5) itself (same arithmetic as ln_rstd(): no separate kernel between the GEMMs)
+    // 1 / sqrt(E[x^2] - E[x]^2 + 1e-5) itself (no separate kernel between the GEMMs)
     const float* ln_stats = nullptr;
     int ln_stats_bs = 0, ln_D = 0;
     // plain fp32-output form only (no residual, no copies): ln_rstd is honoured there too (out = rstd * acc + bias), and
@@ -142,7 +142,6 @@ void layernorm(const float* x, const float* w, const float* b, void* out, bool o
 void convert_f32_bf16(const float* in, bf16* out, long long n, cudaStream_t s);
 // deferred LayerNorm helpers: raw bf16 copy + per-row partial sums of an fp32 stream; weight folding
 void rowstats_convert(const float* x, bf16* out, float* stats, long long rows, int D, cudaStream_t s);
-void ln_rstd(const float* stats, float* rstd, long long rows, int D, cudaStream_t s);  // row sums -> 1 / sqrt(var + 1e-5)
 void fold_ln_weight(const float* W, const float* bias, const float* gamma, const float* beta, bf16* Wf, float* d, int N,
                     int K, bool for_gelu, cudaStream_t s);
 constexpr int LN_PART = 128;  // columns per partial-sum slice (= accumulator columns per GEMM epilogue warp)

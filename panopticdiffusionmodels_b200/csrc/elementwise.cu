@@ -165,27 +165,6 @@ void rowstats_convert(const float* x, bf16* out, float* stats, long long rows, i
     check_launch("rowstats_convert");
 }
 
-// rstd[row] = 1 / sqrt(E[x^2] - E[x]^2 + 1e-5) from the partial row sums (one thread per row; a few MB per call)
-__global__ void __launch_bounds__(256) ln_rstd_kernel(const float2* __restrict__ stats, float* __restrict__ rstd,
-                                                      long long rows, int npart, float invD) {
-    const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= rows) return;
-    float a1 = 0.f, a2 = 0.f;
-    for (int i = 0; i < npart; ++i) {
-        const float2 t = __ldg(stats + row * npart + i);
-        a1 += t.x;
-        a2 += t.y;
-    }
-    const float mean = a1 * invD;
-    const float var = fmaxf(fmaf(-mean, mean, a2 * invD), 0.f);
-    rstd[row] = rsqrtf(var + 1e-5f);
-}
-void ln_rstd(const float* stats, float* rstd, long long rows, int D, cudaStream_t s) {
-    ln_rstd_kernel<<<(unsigned)ceil_div_ll(rows, 256), 256, 0, s>>>((const float2*)stats, rstd, rows,
-                                                                   (D + LN_PART - 1) / LN_PART, 1.f / (float)D);
-    check_launch("ln_rstd");
-}
-
 // Wf[n, k] = bf16(gamma[k] * W[n, k] - m[n]),  m[n] = mean_k(gamma[k] * W[n, k]);   d[n] = bias[n] + sum_k beta[k] * W[n, k]
 // Centring along K costs nothing mathematically (sum_k (x_k - mean) * const = 0) and makes the GEMM itself subtract the row
 // mean: sum_k x_k Wf[n, k] = sum_k (x_k - mean) gamma_k W[n, k], so the consuming epilogue is a single FMA, rstd * acc + d.

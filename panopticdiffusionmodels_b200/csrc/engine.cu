@@ -75,7 +75,6 @@ struct Workspace {
     void* mxb = nullptr;      // act copy of mx    [R2, D]
     float* stats_x = nullptr;   // [R1, ceil(D/128), 2] per-row partial (sum, sum sq) of x  (deferred LayerNorm, bf16 mode)
     float* stats_mx = nullptr;  // [R2, ceil(D/128), 2] same for mx
-    float* rstd = nullptr;      // [max(R1, R2)] 1 / std of the rows the next LN-folded GEMM consumes
     std::vector<void*> skipx; // [depth/2] [R1, D] act
     std::vector<void*> skipm; // [depth/2] [R2, D] act
     float* ctx_all = nullptr; // [nb, T, clip] fp32
@@ -404,7 +403,6 @@ struct pdm_engine {
         const size_t npart = (d + LN_PART - 1) / LN_PART;
         w.stats_x = (float*)a.take(R1 * npart * 2 * 4);
         w.stats_mx = two_m ? (float*)a.take(R2 * npart * 2 * 4) : nullptr;
-        w.rstd = (float*)a.take(R * 4);
         w.skipx.resize(depth / 2);
         w.skipm.resize(two_m ? depth / 2 : 0);
         for (auto& sp : w.skipx) sp = a.take(R1 * d * act);
@@ -1318,7 +1316,7 @@ int pdm_debug_ln_chain(const float* A, const float* W1, const float* b1, const f
         cudaStream_t s = (cudaStream_t)stream;
         const int npart = (D + LN_PART - 1) / LN_PART;
         DevBuf x((size_t)M * D * 4), xb((size_t)M * D * 2), stats((size_t)M * npart * 8);
-        DevBuf wf((size_t)N * D * 2), d((size_t)N * 4), o16((size_t)M * N * 2), rs((size_t)M * 4);
+        DevBuf wf((size_t)N * D * 2), d((size_t)N * 4), o16((size_t)M * N * 2);
         PDM_CHECK_CUDA(cudaMemcpyAsync(x.p, resid, (size_t)M * D * 4, cudaMemcpyDeviceToDevice, s));
         if (A) {
             DevBuf a16((size_t)M * K1 * 2), w16((size_t)D * K1 * 2);

@@ -207,7 +207,7 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 }
 
 // 1 / std of row (b, t) for the LayerNorm-folded forms: a precomputed value, or formed here from the producer's partial row
-// sums with the arithmetic of ln_rstd_kernel (elementwise.cu): mean = S1 / D, var = max(S2 / D - mean^2, 0), rsqrt(var + 1e-5)
+// sums mean = S1 / D, var = max(S2 / D - mean^2, 0), rsqrt(var + 1e-5)
 __device__ __forceinline__ float row_rstd(const TcParams& p, long long b, int t) {
     if (p.ln_stats) {
         const float2* st = reinterpret_cast<const float2*>(p.ln_stats) + (b * p.ln_bs + t) * p.ln_npart;
