@@ -45,23 +45,26 @@ def _digest(paths) -> str:
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ, exist_ok=True)
     extra = os.environ.get("PDM_NVCC_EXTRA", "").split()  # development switches, e.g. -DPDM_ATTN_TRACE
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "pdm.h")]
+    deps = [os.path.join(r, f) for r, _, fs in os.walk(CSRC) for f in fs] + [os.path.join(HERE, "..", "include", "pdm.h")]
     stamp = os.path.join(OBJ, "stamp.txt")
     digest = _digest(deps) + " ".join(extra)
     if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == digest:
         return LIB
     nvcc = _nvcc()
+    sources = list(SOURCES)
+    if "-DPDM_ATTN_EXPERIMENTS" in extra:  # development: measured-and-rejected kernel variants kept for the record
+        sources.append(os.path.join("experiments", "attention_tc4.cu"))
 
     def compile_one(src):
-        obj = os.path.join(OBJ, src.replace(".cu", ".o"))
+        obj = os.path.join(OBJ, os.path.basename(src).replace(".cu", ".o"))
         cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
         return obj, r.stderr
 
-    with cf.ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
-        results = list(ex.map(compile_one, SOURCES))
+    with cf.ThreadPoolExecutor(max_workers=min(8, len(sources))) as ex:
+        results = list(ex.map(compile_one, sources))
     log = os.path.join(OBJ, "ptxas.log")
     with open(log, "w") as f:
         for obj, err in results:

@@ -135,6 +135,9 @@ void gemm_tc_bf16(const GemmProblem& p, cudaStream_t s);
 // ---- attention: qkv [nb, L, 3D] (q | k | v, each H heads x 64) -> out [nb, L, D] ----
 void attention_simt(const void* qkv, void* out, int nb, int L, int H, bool is_bf16, cudaStream_t s);
 void attention_tc_bf16(const bf16* qkv, bf16* out, int nb, int L, int H, cudaStream_t s);
+#ifdef PDM_ATTN_EXPERIMENTS
+void attention_tc4_bf16(const bf16* qkv, bf16* out, int nb, int L, int H, cudaStream_t s);  // experiments/attention_tc4.cu (measured slower; not in the product build)
+#endif
 
 // ---- bandwidth-bound kernels (elementwise.cu) ----
 void layernorm(const float* x, const float* w, const float* b, void* out, bool out_bf16, long long rows, int D,

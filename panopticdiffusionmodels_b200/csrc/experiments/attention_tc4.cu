@@ -1,32 +1,18 @@
-// tcgen05 flash attention v3 (bf16 operands, fp32 softmax / accumulate), head_dim 64, non-causal.
-// Replaces F.scaled_dot_product_attention in libs/uvit_t2i.py:70-74.
-//
-// PERSISTENT: one CTA per SM walks a static list of work items; an item is a PAIR of 128-query tiles:
-//     "same"  items: two consecutive query tiles of one (row, head) -- both tiles share every K/V tile;
-//     "split" items: the ragged last query tile of head 2i paired with the ragged last tile of head 2i+1
-//                    (own K/V tiles each), so an odd tile count (L = 590 -> 5, L = 334 -> 3) costs no idle slot.
-// Tensor memory (512 columns), per tile slot t in {a, b}:  S_t (128 fp32 columns) | P_t (64 columns = 128 bf16) |
-// O_t (64 fp32 columns).  A softmax warpgroup pulls the WHOLE S row into registers first and releases S_t at once
-// (s_free), so Q.K^T of the next key tile runs under the exp2 phase of the current one -- the register file is the
-// second S buffer; nothing on the tensor pipe waits for a softmax except P.V itself.
-//   warps 0-3 / 4-7   softmax warpgroups a / b, one query row per thread: S row -> registers, row max, lazy rescale
-//                     (only when a row max outgrew its reference by > 2^8), exp2 (MUFU, plus an FMA-pipe polynomial
-//                     for a fixed quarter of the scores: the MUFU pipe, 16 ex2/clk/SM, is this kernel's bound),
-//                     P -> TMEM (tcgen05.st).  Chunks of 32 keys beyond L are skipped; warps whose 32 query rows are
-//                     all >= L do nothing.  The O epilogue of an item is deferred under the next item's first tile.
-//   warp 8            TMA producer: Q tiles (double-buffered across items) and a 5-slot ring of (K | V) tiles, all
-//                     straight out of the packed qkv activation [nb, L, 3D] via one 3-D tensor map.
-//   warp 9 / 10       issue O_t += P_t.V (UMMA 128 x 64 x 16, A = P from TMEM, B = V MN-major as it lies in memory)
-//                     and S_t = Q.K^T (UMMA 128 x N x 16, N = 128 or the ragged tail rounded to 16).  The whole warp
-//                     walks the schedule (uniform registers), one elected lane issues.
-// Barrier discipline: a parity wait is only meaningful while the waiter is at most one phase away from the barrier,
-// so every waiter consumes EVERY phase of the barriers it uses, in order.
+// tcgen05 flash attention v4 ("column split"): the tc3 kernel (attention_tc3.cu: persistent items, S / P / O in tensor
+// memory, lazy rescale, polynomial exp2 share) with SIXTEEN softmax warps instead of eight.  A tile slot t is served by TWO
+// warpgroups: warpgroup (t, h) owns key columns [64 h, 64 h + 64) of every score tile -- thread = (query row, half row).  Four
+// softmax warps per scheduler instead of two: the softmax loop is bound by the issue cadence of packed-fp32 code with too few
+// warps to interleave (profiles/r02_attention_trace.md), not by a pipe.  Costs: the two halves of a row exchange their partial
+// row max through shared memory once per tile-step (64-thread named barrier) and their partial row sums once per item; every
+// warp pays the per-step barrier traffic for half the work.
+//   warps 0-3 / 4-7     slot a, halves 0 / 1        warps 8-11 / 12-15   slot b, halves 0 / 1
+//   warp 16 TMA producer, 17 P.V issuer, 18 Q.K^T issuer, 19 idle (setmaxnreg works on whole warpgroups)
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
 
-#include "common.cuh"
-#include "ptx.cuh"
+#include "../common.cuh"
+#include "../ptx.cuh"
 
 namespace pdm {
 
@@ -36,11 +22,12 @@ namespace {
 
 constexpr int QT = 128, KT = 128, HD = 64;
 constexpr int TILE_BYTES = 128 * HD * 2;  // 16 KB
-constexpr int NSLOT = 5;                  // K/V ring slots, (K tile | V tile) each
+constexpr int NSLOT = 4;                  // K/V ring slots, (K tile | V tile) each (one less than tc3: room for the exchange area)
 constexpr int Q_BYTES = 4 * TILE_BYTES;   // 2 item slots x 2 tiles
 constexpr int BAR_BYTES = 256;
-constexpr int SMEM_BYTES = 1024 + Q_BYTES + NSLOT * 2 * TILE_BYTES + BAR_BYTES;
-constexpr int THREADS = 384;  // warps 0-7 softmax, 8 TMA, 9 P.V, 10 Q.K^T, 11 idle (setmaxnreg works on whole warpgroups)
+constexpr int XCH_BYTES = 2 * 2 * 2 * 128 * 4 + 2 * 2 * 128 * 4;  // row-max exchange [parity][slot][half][row] + row-sum exchange [slot][half][row]
+constexpr int SMEM_BYTES = 1024 + Q_BYTES + NSLOT * 2 * TILE_BYTES + BAR_BYTES + XCH_BYTES;
+constexpr int THREADS = 640;  // warps 0-15 softmax, 16 TMA, 17 P.V, 18 Q.K^T, 19 idle
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t S_COL = 0, P_COL = 256, O_COL = 384;  // + t * {128, 64, 64}
 constexpr float RESCALE_LOG2 = 8.f;
@@ -189,25 +176,32 @@ __device__ __forceinline__ void exp2_poly2(float a0, float a1, float& p0, float&
     p1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(t1) << 23));
 }
 
-// One key tile of one query row: S row (NCH chunks of 32 fp32 columns at s_addr) -> registers (then S is handed back:
-// s_free), row max, lazy rescale of the O row, p = exp2((s - m_ref) * scale * log2 e) -> bf16 P at p_addr.
-// MASK: keys >= nvalid of the last chunk count as -inf.
-// wait_prev: the previous P.V of this tile slot (which read P_t and wrote O_t) must have completed (o_full parity).
+// One key tile of one HALF query row: NCH (0..2) chunks of 32 fp32 score columns at s_addr -> registers (then this warp's
+// claim on S is released: s_free), partial row max -> exchanged with the warp that owns the other half, lazy rescale of this
+// warp's 32 O columns, p = exp2((s - m_ref) * scale * log2 e) -> bf16 P at p_addr (NCH x 16 columns), partial row sum.
+// MASK: keys >= nvalid (index inside this half) of the last chunk count as -inf.
 template <int NCH, bool MASK>
-__device__ __forceinline__ void softmax_tile(uint32_t s_addr, uint32_t p_addr, uint32_t o_addr, int nvalid, bool first,
-                                             bool wait_prev, float& m_ref, float& l, uint32_t s_free_bar,
-                                             uint32_t o_full_bar, uint32_t o_full_parity, int lane, bool lockstep TRACE_PARAM) {
+__device__ __forceinline__ void softmax_half(uint32_t s_addr, uint32_t p_addr, uint32_t o_addr, int nvalid, bool first,
+                                             bool wait_prev, float& m_ref, float& l, uint32_t s_free_bar, uint32_t o_full_bar,
+                                             uint32_t o_full_parity, int lane, float* xch_mine, const float* xch_other,
+                                             int pair_bar TRACE_PARAM) {
     const float cs = 0.125f * 1.4426950408889634f;  // softmax scale * log2(e)
-    uint32_t s[NCH][32];
-    // (loading in two halves, to run the row max of the first under the TMEM load of the second, measured 1.5 % slower)
-    constexpr int H1 = NCH;
+    uint32_t s[NCH > 0 ? NCH : 1][32];
 #pragma unroll
-    for (int c = 0; c < H1; ++c) ptx::tmem_ld_32x32(s_addr + c * 32, s[c]);
-    ptx::tmem_ld_wait();
+    for (int c = 0; c < NCH; ++c) ptx::tmem_ld_32x32(s_addr + c * 32, s[c]);
+    if (NCH > 0) ptx::tmem_ld_wait();
+    ptx::tc_fence_before();
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(s_free_bar);  // this warp's share of S_t is in registers
+    TRACE(6, 0);
+    if (MASK && NCH > 0) {
 #pragma unroll
-    for (int c = H1; c < NCH; ++c) ptx::tmem_ld_32x32(s_addr + c * 32, s[c]);
-    float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // four chains: the ALU pipe, not latency, bounds the max
-    auto row_max = [&](int c) {
+        for (int i = 0; i < 32; ++i)
+            if ((NCH - 1) * 32 + i >= nvalid) s[NCH - 1][i] = 0xff800000u;
+    }
+    float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+    for (int c = 0; c < NCH; ++c)
 #pragma unroll
         for (int i = 0; i < 32; i += 8) {
             mx4[0] = max3(mx4[0], __uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1]));
@@ -215,84 +209,63 @@ __device__ __forceinline__ void softmax_tile(uint32_t s_addr, uint32_t p_addr, u
             mx4[2] = max3(mx4[2], __uint_as_float(s[c][i + 4]), __uint_as_float(s[c][i + 5]));
             mx4[3] = max3(mx4[3], __uint_as_float(s[c][i + 6]), __uint_as_float(s[c][i + 7]));
         }
-    };
-    auto mask_tail = [&]() {
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-            if ((NCH - 1) * 32 + i >= nvalid) s[NCH - 1][i] = 0xff800000u;
-    };
-    if (MASK && NCH == H1) mask_tail();
-#pragma unroll
-    for (int c = 0; c < H1; ++c) row_max(c);
-    ptx::tmem_ld_wait();
-    ptx::tc_fence_before();
-    __syncwarp();
-    if (lane == 0) ptx::mbar_arrive(s_free_bar);  // the next Q.K^T of this tile slot may overwrite S now
-    TRACE(6, 0);
-    if (MASK && NCH != H1) mask_tail();
-#pragma unroll
-    for (int c = H1; c < NCH; ++c) row_max(c);
-    const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+    float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+    // the row max over BOTH halves: exchange through shared memory (64-thread named barrier of the two warps of this row quarter)
+    xch_mine[lane] = mx;
+    asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+    mx = fmaxf(mx, xch_other[lane]);
+    TRACE(7, 0);
     if (wait_prev) {
-        // the previous P.V of this slot read P_t and wrote O_t: it must be complete before either is touched.  (Waiting
-        // later, just before the first P store, measured 6 % slower: the wait splits the exp2 schedule.)
-        TRACE(7, 0);
-        ptx::mbar_wait(o_full_bar, o_full_parity);
+        ptx::mbar_wait(o_full_bar, o_full_parity);  // the previous P.V of this slot read P_t and wrote O_t
         ptx::tc_fence_after();
     }
-    // LOCKSTEP: both softmax warpgroups enter their exp2 phase together.  A scheduler hosts one warp of each warpgroup; left
-    // alone the two drift into ANTI-phase -- one in its exp2 phase (issuing at its full single-warp rate, HOLD bits keeping
-    // the issue port), the other crawling through its barrier / TMEM-load / row-max code at a third of its speed -- and the
-    // MUFU pipe only ever serves one warp (clock64 trace: exp 1360 clk, everything else 1680 clk per step, 50 % MUFU busy).
-    // In phase, the exp2 phases share the MUFU pipe and the bookkeeping phases run unstarved side by side.
-    if (lockstep) asm volatile("bar.sync 1, 256;" ::: "memory");
     TRACE(8, 0);
     if (first) {
         m_ref = mx;
     } else if (__any_sync(0xffffffffu, (mx - m_ref) * cs > RESCALE_LOG2)) {
-        // rare: some row outgrew its reference by more than 2^8: rescale l and the O rows accumulated so far
+        // rare: some row outgrew its reference by more than 2^8 (both halves take the same decision: same mx, same m_ref):
+        // rescale this warp's partial l and its 32 columns of the O rows
         const float m_new = fmaxf(m_ref, mx);
         const float corr = ex2((m_ref - m_new) * cs);
+        uint32_t o[32];
+        ptx::tmem_ld_32x32(o_addr, o);
+        ptx::tmem_ld_wait();
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-            uint32_t o[32];
-            ptx::tmem_ld_32x32(o_addr + c * 32, o);
-            ptx::tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * corr);
-            ptx::tmem_st_32x32(o_addr + c * 32, o);
-        }
+        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * corr);
+        ptx::tmem_st_32x32(o_addr, o);
         l *= corr;
         m_ref = m_new;
     }
-    const float nmb = -m_ref * cs;
-    const uint64_t cs2 = pack_f2(cs, cs), nmb2 = pack_f2(nmb, nmb);
-    uint64_t la = pack_f2(0.f, 0.f), lb = la;
+    if (NCH > 0) {
+        const float nmb = -m_ref * cs;
+        const uint64_t cs2 = pack_f2(cs, cs), nmb2 = pack_f2(nmb, nmb);
+        uint64_t la = pack_f2(0.f, 0.f), lb = la;
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-        uint32_t pk[16];
+        for (int c = 0; c < NCH; ++c) {
+            uint32_t pk[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            float a0, a1, p0, p1;
-            unpack_f2(fma2(pack_f2(__uint_as_float(s[c][2 * i]), __uint_as_float(s[c][2 * i + 1])), cs2, nmb2), a0, a1);
-            if (!MASK && ((POLY_PAIRS >> i) & 1)) {
-                exp2_poly2(a0, a1, p0, p1);  // FMA-pipe exp2 for a fixed subset of the pairs: unloads the MUFU pipe
-            } else {
-                p0 = ex2(a0);
-                p1 = ex2(a1);
+            for (int i = 0; i < 16; ++i) {
+                float a0, a1, p0, p1;
+                unpack_f2(fma2(pack_f2(__uint_as_float(s[c][2 * i]), __uint_as_float(s[c][2 * i + 1])), cs2, nmb2), a0, a1);
+                if (!MASK && ((POLY_PAIRS >> i) & 1)) {
+                    exp2_poly2(a0, a1, p0, p1);
+                } else {
+                    p0 = ex2(a0);
+                    p1 = ex2(a1);
+                }
+                if (i & 1) lb = add2(lb, pack_f2(p0, p1)); else la = add2(la, pack_f2(p0, p1));
+                pk[i] = pack_bf16(p0, p1);
             }
-            if (i & 1) lb = add2(lb, pack_f2(p0, p1)); else la = add2(la, pack_f2(p0, p1));
-            pk[i] = pack_bf16(p0, p1);
+            ptx::tmem_st_32x32_x16(p_addr + c * 16, pk);
         }
-        ptx::tmem_st_32x32_x16(p_addr + c * 16, pk);
+        float x0, x1;
+        unpack_f2(add2(la, lb), x0, x1);
+        l += x0 + x1;
     }
-    float x0, x1;
-    unpack_f2(add2(la, lb), x0, x1);
-    l += x0 + x1;
 }
 
 __global__ void __launch_bounds__(THREADS, 1)
-attention_tc3_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__ out, const Shape sh) {
+attention_tc4_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__ out, const Shape sh) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);  // SWIZZLE_128B tiles: 1024 B
     uint8_t* sQ = smem;               // [2 item slots][2 tiles]
@@ -308,6 +281,7 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict
     uint64_t* o_full = p_full + 2;            // [2]      P.V commit -> softmax warpgroup t (P_t consumed, O_t updated)
     uint64_t* o_empty = o_full + 2;           // [2]      softmax warpgroup t (4 warps) -> P.V warp: O_t drained
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 2);
+    float* xch = reinterpret_cast<float*>(smem + Q_BYTES + NSLOT * 2 * TILE_BYTES + BAR_BYTES);  // [2][2][2][128] max | [2][2][128] sum
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int D = sh.H * HD;
@@ -322,10 +296,10 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict
             ptx::mbar_init(&q_full[i], 1);
             ptx::mbar_init(&q_empty[i], 1);
             ptx::mbar_init(&s_full[i], 1);
-            ptx::mbar_init(&s_free[i], 4);
-            ptx::mbar_init(&p_full[i], 4);
+            ptx::mbar_init(&s_free[i], 8);
+            ptx::mbar_init(&p_full[i], 8);
             ptx::mbar_init(&o_full[i], 1);
-            ptx::mbar_init(&o_empty[i], 4);
+            ptx::mbar_init(&o_empty[i], 8);
         }
         for (int i = 0; i < NSLOT; ++i) {
             ptx::mbar_init(&kv_full[i], 1);
@@ -333,7 +307,7 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict
         }
         ptx::fence_mbar_init();
     }
-    if (warp == 9) {
+    if (warp == 17) {
         ptx::tmem_alloc(tmem_slot, TMEM_COLS);
         ptx::tmem_relinquish();
     }
@@ -342,7 +316,7 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp >= 8) {
+    if (warp >= 16) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
         // Producer and MMA warps: the WHOLE warp walks the schedule (warp-uniform control flow and operands, so the
         // descriptors live in uniform registers); only the TMA / tcgen05.mma / tcgen05.commit instructions are issued
@@ -353,7 +327,7 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict
         const uint32_t sKV_u = __shfl_sync(0xffffffffu, ptx::smem_u32(sKV), 0);
         ItemWalk w;
         w.init(sh);
-        if (warp == 8) {
+        if (warp == 16) {
             // ===================== TMA producer =====================
             Ring ring;
             int qi = 0;
@@ -386,7 +360,7 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict
                 }
                 ++qi;
             }
-        } else if (warp == 10) {
+        } else if (warp == 18) {
             // ===================== S_t = Q.K^T issuer =====================
             const uint32_t idesc_qk_full = ptx::make_idesc_bf16(QT, KT, 0, 0);
             const uint32_t idesc_qk_last = ptx::make_idesc_bf16(QT, sh.last_n16, 0, 0);
@@ -427,7 +401,7 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict
                 }
                 ++qi;
             }
-        } else if (warp == 9) {
+        } else if (warp == 17) {
             // ===================== O_t += P_t.V issuer =====================
             constexpr uint32_t idesc_pv = ptx::make_idesc_bf16(QT, HD, 0, 1);  // A = P (TMEM), B = V MN-major
             const int ksteps_last = sh.last_n16 / 16;
@@ -478,64 +452,70 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict
             }
         }
     } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
-        // ===================== softmax warpgroups: thread <-> query row =====================
-        const int t = warp >> 2;  // tile slot handled by this warpgroup
-        const int wq = warp & 3;
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");  // pool = 640 x 96 launch registers: 512 x 104 + 128 x 56 fits, 112 would block forever
+        // ===================== softmax warpgroups: thread <-> (query row, half of the key columns) =====================
+        const int t = warp >> 3;         // tile slot
+        const int hf = (warp >> 2) & 1;  // which 64 key columns of every score tile
+        const int wq = warp & 3;         // TMEM lane quarter = 32 query rows
         const uint32_t lane_base = uint32_t(wq * 32) << 16;
-        const uint32_t s_addr = tmem_base + lane_base + S_COL + t * 128;
-        const uint32_t p_addr = tmem_base + lane_base + P_COL + t * 64;
-        const uint32_t o_addr = tmem_base + lane_base + O_COL + t * 64;
-        const int nch_last = (sh.last_n16 + 31) >> 5;  // 32-key chunks of the ragged last key tile that P.V reads
-        uint32_t steps = 0;    // tile-steps of slot t completed so far (phase counter of s_full / o_full)
+        const uint32_t s_addr = tmem_base + lane_base + S_COL + t * 128 + hf * 64;
+        const uint32_t p_addr = tmem_base + lane_base + P_COL + t * 64 + hf * 32;
+        const uint32_t o_addr = tmem_base + lane_base + O_COL + t * 64 + hf * 32;
+        // 32-key chunks of this half in the ragged last key tile, and the valid keys inside the half
+        const int nch_all = (sh.last_n16 + 31) >> 5;
+        const int nch_last = min(2, max(0, nch_all - 2 * hf));
+        const int nv_half = sh.last_valid - 64 * hf;
+        uint32_t steps = 0;  // tile-steps of slot t completed so far (phase counter of s_full / o_full)
         const uint32_t b_s_full = ptx::smem_u32(&s_full[t]), b_s_free = ptx::smem_u32(&s_free[t]);
         const uint32_t b_p_full = ptx::smem_u32(&p_full[t]), b_o_full = ptx::smem_u32(&o_full[t]);
         const uint32_t b_o_empty = ptx::smem_u32(&o_empty[t]);
+        const int pair_bar = 1 + t * 4 + wq;  // named barrier of the two warps (halves 0 / 1) of this slot and row quarter
+        float* xmax = xch;                    // [parity][slot][half][128]
+        float* xsum = xch + 2 * 2 * 2 * 128;  // [slot][half][128]
+        float* xsum_mine = xsum + (t * 2 + hf) * 128 + wq * 32;
+        const float* xsum_other = xsum + (t * 2 + (hf ^ 1)) * 128 + wq * 32;
 
-        // The O epilogue of an item is DEFERRED until this warpgroup has pushed the first key tile of its next item
-        // through the softmax: the O -> global stores then sit under the MMAs / exp2 of the neighbouring work instead
-        // of leaving the MUFU pipe idle at every item boundary.
         struct Pending {
             bool any = false, live = false, row_ok = false;
             uint32_t parity = 0;
-            float inv_l = 0.f;
+            float l = 0.f;
             bf16* dst = nullptr;
         } pend;
-        auto flush_epilogue = [&]() {  // O / l -> bf16 rows of the pending item
+        auto flush_epilogue = [&]() {  // this warp's 32 columns of O / l -> bf16 rows of the pending item
             ptx::mbar_wait(b_o_full, pend.parity);  // the item's last P.V has landed
             ptx::tc_fence_after();
             TRACE(4, 0);
+            // total row sum = both halves
+            xsum_mine[lane] = pend.l;
+            asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+            const float inv = 1.f / (pend.l + xsum_other[lane]);
             if (pend.live) {
-                uint32_t v[2][32];
-                ptx::tmem_ld_32x32(o_addr, v[0]);
-                ptx::tmem_ld_32x32(o_addr + 32, v[1]);
+                uint32_t v[32];
+                ptx::tmem_ld_32x32(o_addr, v);
                 ptx::tmem_ld_wait();
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(b_o_empty);  // O_t may be overwritten by the next item
                 if (pend.row_ok) {
-                    const float inv = pend.inv_l;
-                    // one thread owns one 128-byte output row segment: four 256-bit stores (STG.256)
 #pragma unroll
-                    for (int c = 0; c < 2; ++c)
+                    for (int q = 0; q < 2; ++q) {
+                        uint32_t pk[8];
 #pragma unroll
-                        for (int q = 0; q < 2; ++q) {
-                            uint32_t pk[8];
-#pragma unroll
-                            for (int e = 0; e < 8; ++e)
-                                pk[e] = pack_bf16(__uint_as_float(v[c][16 * q + 2 * e]) * inv,
-                                                  __uint_as_float(v[c][16 * q + 2 * e + 1]) * inv);
-                            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
-                                         ::"l"(pend.dst + c * 32 + q * 16), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]),
-                                         "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7])
-                                         : "memory");
-                        }
+                        for (int e = 0; e < 8; ++e)
+                            pk[e] = pack_bf16(__uint_as_float(v[16 * q + 2 * e]) * inv, __uint_as_float(v[16 * q + 2 * e + 1]) * inv);
+                        asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                                     ::"l"(pend.dst + q * 16), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]), "r"(pk[4]), "r"(pk[5]),
+                                     "r"(pk[6]), "r"(pk[7])
+                                     : "memory");
+                    }
                 }
             } else {
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(b_o_empty);
             }
+            // the exchange slot is reused by the next item's epilogue: both warps must have read it
+            asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
             pend.any = false;
             TRACE(5, 0);
         };
@@ -556,21 +536,19 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict
                     ptx::mbar_wait(b_s_full, steps & 1);
                     ptx::tc_fence_after();
                     TRACE(1, steps);
-                    // before P_t is rewritten / O_t rescaled, the previous P.V of this slot must be complete: the previous
-                    // key tile's (j > 0) or the previous item's last one (same phase the deferred epilogue waits for)
                     const bool wait_prev = j > 0 || pend.any;
-                    const bool lockstep = LOCKSTEP && nt == 2;  // both warpgroups walk this item
                     const uint32_t ofp = (steps - 1) & 1;
+                    float* xm_mine = xmax + (((steps & 1) * 2 + t) * 2 + hf) * 128 + wq * 32;
+                    const float* xm_other = xmax + (((steps & 1) * 2 + t) * 2 + (hf ^ 1)) * 128 + wq * 32;
                     if (live) {
                         if (j < nkv - 1) {
-                            softmax_tile<4, false>(s_addr, p_addr, o_addr, KT, j == 0, wait_prev, m_ref, l, b_s_free, b_o_full, ofp, lane, lockstep TRACE_ARG);
+                            softmax_half<2, false>(s_addr, p_addr, o_addr, 64, j == 0, wait_prev, m_ref, l, b_s_free, b_o_full, ofp, lane,
+                                                   xm_mine, xm_other, pair_bar TRACE_ARG);
                         } else {
-                            const int nv = sh.last_valid;
                             switch (nch_last) {
-                                case 1: softmax_tile<1, true>(s_addr, p_addr, o_addr, nv, j == 0, wait_prev, m_ref, l, b_s_free, b_o_full, ofp, lane, lockstep TRACE_ARG); break;
-                                case 2: softmax_tile<2, true>(s_addr, p_addr, o_addr, nv, j == 0, wait_prev, m_ref, l, b_s_free, b_o_full, ofp, lane, lockstep TRACE_ARG); break;
-                                case 3: softmax_tile<3, true>(s_addr, p_addr, o_addr, nv, j == 0, wait_prev, m_ref, l, b_s_free, b_o_full, ofp, lane, lockstep TRACE_ARG); break;
-                                default: softmax_tile<4, true>(s_addr, p_addr, o_addr, nv, j == 0, wait_prev, m_ref, l, b_s_free, b_o_full, ofp, lane, lockstep TRACE_ARG); break;
+                                case 0: softmax_half<0, true>(s_addr, p_addr, o_addr, nv_half, j == 0, wait_prev, m_ref, l, b_s_free, b_o_full, ofp, lane, xm_mine, xm_other, pair_bar TRACE_ARG); break;
+                                case 1: softmax_half<1, true>(s_addr, p_addr, o_addr, nv_half, j == 0, wait_prev, m_ref, l, b_s_free, b_o_full, ofp, lane, xm_mine, xm_other, pair_bar TRACE_ARG); break;
+                                default: softmax_half<2, true>(s_addr, p_addr, o_addr, nv_half, j == 0, wait_prev, m_ref, l, b_s_free, b_o_full, ofp, lane, xm_mine, xm_other, pair_bar TRACE_ARG); break;
                             }
                         }
                         TRACE(2, steps);
@@ -578,15 +556,12 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict
                     } else {
                         if (lane == 0) ptx::mbar_arrive(b_s_free);
                         if (wait_prev) ptx::mbar_wait(b_o_full, ofp);  // keep in step with o_full
-                        if (lockstep) asm volatile("bar.sync 1, 256;" ::: "memory");
                     }
                     ptx::tc_fence_before();
                     __syncwarp();
                     if (lane == 0) ptx::mbar_arrive(b_p_full);
                     TRACE(3, steps);
                     ++steps;
-                    // the previous item's epilogue, now that this item's first P is on its way (P.V of j = 0 waits for
-                    // o_empty, i.e. for the O loads of the epilogue)
                     if (j == 0 && pend.any) flush_epilogue();
                 }
                 const int qi = q0 + wq * 32 + lane;
@@ -594,8 +569,8 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict
                 pend.live = live;
                 pend.row_ok = qi < sh.L;
                 pend.parity = (steps - 1) & 1;
-                pend.inv_l = 1.f / l;
-                pend.dst = out + ((long long)b * sh.L + qi) * D + h * HD;
+                pend.l = l;
+                pend.dst = out + ((long long)b * sh.L + qi) * D + h * HD + hf * 32;
             } else if (pend.any) {
                 flush_epilogue();  // this tile slot sits the item out (odd head count)
             }
@@ -605,7 +580,7 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict
 
     ptx::tc_fence_before();
     __syncthreads();
-    if (warp == 9) {
+    if (warp == 17) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc(tmem_base, TMEM_COLS);
     }
@@ -613,18 +588,11 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict
 
 }  // namespace
 
-void attention_tc_bf16(const bf16* qkv, bf16* out, int nb, int L, int H, cudaStream_t s) {
-#ifdef PDM_ATTN_EXPERIMENTS  // development builds only (PDM_NVCC_EXTRA=-DPDM_ATTN_EXPERIMENTS): experiments/attention_tc4.cu
-    static const bool v4 = getenv("PDM_ATTN_V4") != nullptr;
-    if (v4) {
-        attention_tc4_bf16(qkv, out, nb, L, H, s);
-        return;
-    }
-#endif
+void attention_tc4_bf16(const bf16* qkv, bf16* out, int nb, int L, int H, cudaStream_t s) {
     const int D = H * HD;
     const CUtensorMap tm = make_tmap_bf16_3d(qkv, 3LL * D, L, nb, L, 128, HD);
     static std::atomic<bool> attr_set[MAX_DEVICES];
-    ensure_dyn_smem(attention_tc3_kernel, SMEM_BYTES, attr_set);
+    ensure_dyn_smem(attention_tc4_kernel, SMEM_BYTES, attr_set);
     Shape sh;
     sh.L = L;
     sh.H = H;
@@ -647,7 +615,7 @@ void attention_tc_bf16(const bf16* qkv, bf16* out, int nb, int L, int H, cudaStr
     }
     PDM_CHECK_CUDA(cudaMemsetAsync(trace, 0, 12 * 4096 * 8, s));
 #endif
-    attention_tc3_kernel<<<grid, THREADS, SMEM_BYTES, s>>>(tm, out, sh);
+    attention_tc4_kernel<<<grid, THREADS, SMEM_BYTES, s>>>(tm, out, sh);
     check_launch("attention_tc3");
 #ifdef PDM_ATTN_TRACE
     if (const char* f = getenv("PDM_ATTN_TRACE_FILE")) {
