@@ -937,11 +937,34 @@ struct pdm_engine {
         if (has_mask && pfin != ws.P0) PDM_CHECK_CUDA(cudaMemcpyAsync(ws.P0, pfin, n_msk * 4, cudaMemcpyDeviceToDevice, s));
     }
 
+    // A plan is host data from the caller: refuse one the loop cannot execute instead of reading stale buffers.
+    static void validate_plan(const float* plan, int n_evals) {
+        const bool multistep = plan[15] != 0.f;
+        bool step_open = false;  // singlestep: inside a step (the previous record was not its last)
+        int prev_stage = -1;
+        for (int k = 0; k < n_evals; ++k) {
+            const float* r = plan + (size_t)k * PDM_PLAN_STRIDE;
+            for (int i = 0; i < PDM_PLAN_STRIDE; ++i)
+                PDM_REQUIRE(std::isfinite(r[i]), "pdm_sample: non-finite value in plan record " + std::to_string(k));
+            PDM_REQUIRE((r[15] != 0.f) == multistep, "pdm_sample: a plan must not mix singlestep and multistep records");
+            if (multistep) continue;  // orders are checked where they are used
+            const int stage = (int)r[8];
+            PDM_REQUIRE(stage >= 0 && stage <= 2 && (float)stage == r[8], "pdm_sample: bad stage in plan record " + std::to_string(k));
+            PDM_REQUIRE(stage == (step_open ? prev_stage + 1 : 0),
+                        "pdm_sample: stage out of sequence in plan record " + std::to_string(k) +
+                            " (a step starts at stage 0 and its stages are consecutive)");
+            step_open = r[10] == 0.f;
+            prev_stage = stage;
+        }
+        PDM_REQUIRE(multistep || !step_open, "pdm_sample: the plan ends inside a step (last record must close its step)");
+    }
+
     void sample(const float* plan, int n_evals, const float* z_init, const float* mask_init, const float* ctx,
                 const float* empty_ctx, float scale, float* out_z, float* out_pm, int B, int prec, bool use_graph,
                 cudaStream_t s) {
         PDM_REQUIRE(finalized, "parameters not finalized");
         PDM_REQUIRE(n_evals > 0 && B > 0, "bad sample arguments");
+        validate_plan(plan, n_evals);
         const bool has_mask = mask_init != nullptr;
         PDM_REQUIRE(!has_mask || cfg.enable_panoptic, "model built with enable_panoptic=False cannot take a mask");
         PDM_REQUIRE(!has_mask || out_pm, "out_pred_mask required");

@@ -248,6 +248,8 @@ class UViT(nn.Module):
             if tuple(mask_token.shape) != (B, self.num_panoptic_class, self.img_size, self.img_size):
                 raise ValueError("mask_token must be (B, num_panoptic_class, img_size, img_size) (SURVEY F4)")
             y = torch.empty_like(mask_token)
+        if B == 0:  # an empty batch flows through the reference's torch ops as empty tensors; nothing to launch
+            return noise if y is None else (noise, y)
         with torch.cuda.device(dev):
             flags = _lib.FWD_GROUND_TRUTH if (use_ground_truth and mask_token is not None) else 0
             _lib.check(_lib.lib().pdm_nnet_forward_ex(

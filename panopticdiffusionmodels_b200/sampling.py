@@ -93,6 +93,10 @@ class CFGModel:
         out_z = torch.empty_like(z)
         out_pm = None if m is None else torch.empty_like(m)
         plan = np.ascontiguousarray(plan, dtype=np.float32)
+        if z.shape[0] == 0:  # empty shard (e.g. a rank past the end of the prompt list): nothing to launch
+            return out_z, out_pm
+        if plan.shape[0] == 0:  # steps < order with method='singlestep': the reference's loop body never runs
+            return z.clone(), (None if m is None else m.clone())
         with torch.cuda.device(dev):
             _lib.check(_lib.lib().pdm_sample(
                 h, plan.ctypes.data_as(C.POINTER(C.c_float)), plan.shape[0], _lib.ptr(z), _lib.ptr(m), _lib.ptr(ctx),

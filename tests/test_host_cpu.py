@@ -80,6 +80,26 @@ def test_no_cpu_fallback():
         P.DPM_Solver(lambda *a, **k: None, ns, predict_x0=True).sample(x, steps=6, eps=1e-3, T=1.0)
 
 
+def test_c_abi_null_arguments_return_a_status_not_a_crash():
+    """Every entry point reports bad arguments through its int status + pdm_last_error() before touching the device
+    (include/pdm.h: 0 = OK); none of these calls computes anything, so they are safe without a GPU."""
+    import ctypes as C
+    from panopticdiffusionmodels_b200 import _lib
+    L = _lib.lib()
+    assert L.pdm_abi_version() == _lib.ABI_VERSION
+    h = C.c_void_p()
+    assert L.pdm_create(None, C.byref(h)) != 0 and "null" in L.pdm_last_error().decode()
+    assert L.pdm_set_param(None, b"pos_embed", None, None, 0, None) != 0
+    assert L.pdm_finalize_params(None, None) != 0 and "null" in L.pdm_last_error().decode()
+    n = C.c_size_t()
+    assert L.pdm_workspace_bytes(None, 4, 0, C.byref(n)) != 0
+    assert L.pdm_nnet_forward(None, None, None, None, None, None, None, 1, 0, None) != 0
+    assert L.pdm_sample(None, None, 0, None, None, None, None, 1.0, None, None, 1, 0, 1, None) != 0
+    assert L.pdm_vae_create(None, C.byref(h)) != 0
+    assert L.pdm_vae_decode(None, None, None, 1, 32, None) != 0
+    assert L.pdm_destroy(None) == 0  # destroying nothing is fine
+
+
 def test_rejected_options():
     from panopticdiffusionmodels_b200.libs.uvit_t2i import UViT
     with pytest.raises(NotImplementedError):
