@@ -87,136 +87,189 @@ __global__ void gn_finalize_kernel(const float* __restrict__ part, float* __rest
     mr[2 * i] = (float)mean;
     mr[2 * i + 1] = (float)(1.0 / sqrt(var + (double)eps));
 }
-__device__ __forceinline__ float swish(float v) { return v / (1.f + __expf(-v)); }
-// y = GN(x) [* sigmoid(.)] -> bf16 NHWC (the next convolution's operand)
+__device__ __forceinline__ float swish(float v) { return __fdividef(v, 1.f + __expf(-v)); }
+__device__ __forceinline__ uint2 pack4_bf16(float y0, float y1, float y2, float y3) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(y0, y1), b = __floats2bfloat162_rn(y2, y3);
+    return make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+}
+// y = GN(x) [* sigmoid(.)] -> bf16 NHWC (the next convolution's operand).  Grid (pixel slabs, images); a thread keeps ONE
+// float4 channel column for the whole slab, so mean / 1/std / gamma / beta collapse into a per-thread (scale, shift) pair read
+// once, and the slab is walked with 32-bit indices, four independent 16-byte loads in flight (HBM-bound: 6 B per element).
 __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__ x, const float* __restrict__ mr,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                       bf16* __restrict__ out, long long total4, int hw, int C, int act) {
+                                                       bf16* __restrict__ out, int hw, int C, int act, int pix_per_block) {
+    const int n = blockIdx.y;
     const int c4n = C >> 2, cpg = C / GN_GROUPS;
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (; i < total4; i += stride) {
-        const int col = (int)(i % c4n);
-        const long long pix = i / c4n;
-        const int n = (int)(pix / hw);
-        const int g = (col * 4) / cpg;
-        const float mean = mr[((long long)n * GN_GROUPS + g) * 2], rstd = mr[((long long)n * GN_GROUPS + g) * 2 + 1];
-        const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
-        const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma) + col), be = __ldg(reinterpret_cast<const float4*>(beta) + col);
-        float y0 = (v.x - mean) * rstd * ga.x + be.x, y1 = (v.y - mean) * rstd * ga.y + be.y;
-        float y2 = (v.z - mean) * rstd * ga.z + be.z, y3 = (v.w - mean) * rstd * ga.w + be.w;
+    const int col = threadIdx.x % c4n, prow = threadIdx.x / c4n, pstep = blockDim.x / c4n;
+    if (prow >= pstep) return;
+    const int g = (col * 4) / cpg;
+    const float mean = mr[((long long)n * GN_GROUPS + g) * 2], rstd = mr[((long long)n * GN_GROUPS + g) * 2 + 1];
+    const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma) + col), be = __ldg(reinterpret_cast<const float4*>(beta) + col);
+    const float4 sc = make_float4(rstd * ga.x, rstd * ga.y, rstd * ga.z, rstd * ga.w);
+    const float4 sh = make_float4(fmaf(-mean, sc.x, be.x), fmaf(-mean, sc.y, be.y), fmaf(-mean, sc.z, be.z), fmaf(-mean, sc.w, be.w));
+    const int p0 = blockIdx.x * pix_per_block, p1 = min(hw, p0 + pix_per_block);
+    const float4* src = reinterpret_cast<const float4*>(x) + (long long)n * hw * c4n + col;
+    uint2* dst = reinterpret_cast<uint2*>(out) + (long long)n * hw * c4n + col;
+    auto one = [&](const float4 v, int p) {
+        float y0 = fmaf(v.x, sc.x, sh.x), y1 = fmaf(v.y, sc.y, sh.y), y2 = fmaf(v.z, sc.z, sh.z), y3 = fmaf(v.w, sc.w, sh.w);
         if (act) { y0 = swish(y0); y1 = swish(y1); y2 = swish(y2); y3 = swish(y3); }
-        __nv_bfloat162 a = __floats2bfloat162_rn(y0, y1), b = __floats2bfloat162_rn(y2, y3);
-        reinterpret_cast<uint2*>(out)[i] = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+        dst[(long long)p * c4n] = pack4_bf16(y0, y1, y2, y3);
+    };
+    int p = p0 + prow;
+    for (; p + 3 * pstep < p1; p += 4 * pstep) {
+        const float4 v0 = __ldg(src + (long long)p * c4n), v1 = __ldg(src + (long long)(p + pstep) * c4n);
+        const float4 v2 = __ldg(src + (long long)(p + 2 * pstep) * c4n), v3 = __ldg(src + (long long)(p + 3 * pstep) * c4n);
+        one(v0, p); one(v1, p + pstep); one(v2, p + 2 * pstep); one(v3, p + 3 * pstep);
     }
+    for (; p < p1; p += pstep) one(__ldg(src + (long long)p * c4n), p);
 }
-// fp32 NHWC -> bf16 NHWC, optionally through a nearest-neighbour 2x upsample (F.interpolate(scale_factor=2, 'nearest'))
-__global__ void __launch_bounds__(256) convert_up_kernel(const float* __restrict__ x, bf16* __restrict__ out, long long total4,
-                                                         int H, int W, int C, int up) {
+// fp32 NHWC -> bf16 NHWC, optionally through a nearest-neighbour 2x upsample (F.interpolate(scale_factor=2, 'nearest')).
+// Grid (output rows n * Ho, ceil(Wo * C/4 / 256)): 32-bit index arithmetic only.
+__global__ void __launch_bounds__(256) convert_up_kernel(const float* __restrict__ x, bf16* __restrict__ out, int H, int W, int C,
+                                                         int up) {
     const int c4n = C >> 2;
     const int Ho = up ? 2 * H : H, Wo = up ? 2 * W : W;
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (; i < total4; i += stride) {
-        const int col = (int)(i % c4n);
-        long long pix = i / c4n;
-        const int wo = (int)(pix % Wo);
-        pix /= Wo;
-        const int ho = (int)(pix % Ho);
-        const long long n = pix / Ho;
-        const int h = up ? ho >> 1 : ho, w = up ? wo >> 1 : wo;
-        const float4 v = __ldg(reinterpret_cast<const float4*>(x) + ((n * H + h) * W + w) * c4n + col);
-        __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
-        reinterpret_cast<uint2*>(out)[i] = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
-    }
+    const int e = blockIdx.y * blockDim.x + threadIdx.x;  // (wo, col) within the output row
+    if (e >= Wo * c4n) return;
+    const int wo = e / c4n, col = e - wo * c4n;
+    const int row = blockIdx.x, n = row / Ho, ho = row - n * Ho;
+    const int h = up ? ho >> 1 : ho, w = up ? wo >> 1 : wo;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x) + ((long long)(n * H + h) * W + w) * c4n + col);
+    reinterpret_cast<uint2*>(out)[(long long)row * Wo * c4n + e] = pack4_bf16(v.x, v.y, v.z, v.w);
 }
 
 // ---------------------------------------------------------------------------------------------- the two narrow convolutions
 // z [n, Cz, h, w] (NCHW fp32) -> z / scale -> post_quant_conv (1x1) -> conv_in (3x3, pad 1) -> x [n, h, w, Cout] (NHWC fp32).
-// One thread per (pixel, 4 output channels); the 3x3 x Cz neighbourhood after the 1x1 is rebuilt per thread (Cz = 4).
+// A block owns CIN_PX consecutive pixels of one row: the post_quant output of their 3 x (CIN_PX + 2) neighbourhood is built
+// once in shared memory (zero outside the image: the 3x3 pads ITS input), then every thread keeps 4 output channels for all
+// CIN_PX pixels and walks the 9 taps with that tap's 4 x Cz weights in registers.
+constexpr int CIN_PX = 8;
 template <int CZ>
 __global__ void __launch_bounds__(128) conv_in_kernel(const float* __restrict__ z, const float* __restrict__ pq_w,
                                                       const float* __restrict__ pq_b, const float* __restrict__ w,
                                                       const float* __restrict__ b, float* __restrict__ out, int n, int H, int W,
                                                       int Cout, float inv_scale) {
-    const int c4n = Cout >> 2;
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (long long)n * H * W * c4n) return;
-    const int col = (int)(i % c4n);
-    long long pix = i / c4n;
-    const int x0 = (int)(pix % W);
-    pix /= W;
-    const int y0 = (int)(pix % H);
-    const int img = (int)(pix / H);
-    float acc[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) acc[k] = __ldg(b + col * 4 + k);
-    for (int ky = 0; ky < 3; ++ky) {
-        const int yy = y0 + ky - 1;
-        if (yy < 0 || yy >= H) continue;
-        for (int kx = 0; kx < 3; ++kx) {
-            const int xx = x0 + kx - 1;
-            if (xx < 0 || xx >= W) continue;
-            float zin[CZ], pq[CZ];
+    static_assert(CZ == 4, "post_quant output is read back as float4");
+    __shared__ float4 pq[3][CIN_PX + 2];
+    const int segs = (W + CIN_PX - 1) / CIN_PX;
+    const int seg = blockIdx.x % segs, y0 = (blockIdx.x / segs) % H, img = blockIdx.x / (segs * H);
+    const int xb = seg * CIN_PX;
+    if (threadIdx.x < 3 * (CIN_PX + 2)) {
+        const int ky = threadIdx.x / (CIN_PX + 2), j = threadIdx.x % (CIN_PX + 2);
+        const int yy = y0 + ky - 1, xx = xb + j - 1;
+        float v[CZ] = {0.f, 0.f, 0.f, 0.f};
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+            float zin[CZ];
 #pragma unroll
             for (int c = 0; c < CZ; ++c) zin[c] = __ldg(z + (((long long)img * CZ + c) * H + yy) * W + xx) * inv_scale;
 #pragma unroll
             for (int o = 0; o < CZ; ++o) {
-                float v = __ldg(pq_b + o);
+                float t = __ldg(pq_b + o);
 #pragma unroll
-                for (int c = 0; c < CZ; ++c) v = fmaf(__ldg(pq_w + o * CZ + c), zin[c], v);
-                pq[o] = v;
-            }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const float* wr = w + (((long long)(col * 4 + k) * CZ) * 3 + ky) * 3 + kx;  // [Cout, CZ, 3, 3]
-#pragma unroll
-                for (int c = 0; c < CZ; ++c) acc[k] = fmaf(__ldg(wr + c * 9), pq[c], acc[k]);
+                for (int c = 0; c < CZ; ++c) t = fmaf(__ldg(pq_w + o * CZ + c), zin[c], t);
+                v[o] = t;
             }
         }
-    }
-    reinterpret_cast<float4*>(out)[i] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-}
-// conv_out: bf16 NHWC [n, H, W, C] (already GroupNorm'ed + swish) -> 3x3 -> out [n, Co, H, W] (NCHW fp32), Co <= 4.
-// One thread per output pixel; weights staged in shared memory as [tap][c][Co].
-__global__ void __launch_bounds__(128) conv_out_kernel(const bf16* __restrict__ a, const float* __restrict__ w,
-                                                       const float* __restrict__ b, float* __restrict__ out, int n, int H, int W,
-                                                       int C, int Co) {
-    extern __shared__ float wsm[];  // [9][C][4]
-    for (int i = threadIdx.x; i < 9 * C * 4; i += blockDim.x) {
-        const int o = i & 3, c = (i >> 2) % C, tap = (i >> 2) / C;
-        wsm[i] = o < Co ? w[((long long)(o * C + c)) * 9 + tap] : 0.f;  // [Co, C, 3, 3]
+        pq[ky][j] = make_float4(v[0], v[1], v[2], v[3]);
     }
     __syncthreads();
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (long long)n * H * W) return;
-    const int x0 = (int)(i % W), y0 = (int)((i / W) % H);
-    const long long img = i / ((long long)W * H);
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const int c4n = Cout >> 2;
+    for (int col = threadIdx.x; col < c4n; col += blockDim.x) {
+        float acc[CIN_PX][4];
+        const float4 bias = __ldg(reinterpret_cast<const float4*>(b) + col);
+#pragma unroll
+        for (int px = 0; px < CIN_PX; ++px) { acc[px][0] = bias.x; acc[px][1] = bias.y; acc[px][2] = bias.z; acc[px][3] = bias.w; }
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+            const int ky = tap / 3, kx = tap % 3;
+            float wr[4][CZ];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+#pragma unroll
+                for (int c = 0; c < CZ; ++c) wr[k][c] = __ldg(w + ((long long)(col * 4 + k) * CZ + c) * 9 + tap);  // [Cout, CZ, 3, 3]
+#pragma unroll
+            for (int px = 0; px < CIN_PX; ++px) {
+                const float4 q = pq[ky][px + kx];
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    acc[px][k] = fmaf(wr[k][0], q.x, fmaf(wr[k][1], q.y, fmaf(wr[k][2], q.z, fmaf(wr[k][3], q.w, acc[px][k]))));
+            }
+        }
+#pragma unroll
+        for (int px = 0; px < CIN_PX; ++px)
+            if (xb + px < W)
+                reinterpret_cast<float4*>(out)[((long long)(img * H + y0) * W + xb + px) * c4n + col] =
+                    make_float4(acc[px][0], acc[px][1], acc[px][2], acc[px][3]);
+    }
+}
+// conv_out: bf16 NHWC [n, H, W, C] (already GroupNorm'ed + swish) -> 3x3 -> out [n, Co, H, W] (NCHW fp32), Co <= 4.
+// Three output channels are far below a tcgen05 tile (N >= 16 of a 128-row tile would be 80 % padding), so this one runs on
+// warp-level mma.sync m16n8k16 (bf16 in, fp32 accumulate): a warp owns 16 consecutive pixels of a row, K walks
+// 9 taps x C channels.  A fragments come straight from global memory as 16-byte loads -- lane (g, t) reads channels
+// [32 cb + 8 t, + 8) of pixels g and g + 8, and the K slots of two consecutive MMAs are ASSIGNED to those channels
+// (slot 2t+j <-> channel 8t+4s+j, slot 2t+8+j <-> channel 8t+4s+2+j); the weights are staged in shared memory already in
+// that per-lane fragment order (one 8-byte LDS per MMA).  Block = 8 warps = 4 rows x 32 pixels.
+__global__ void __launch_bounds__(256) conv_out_kernel(const bf16* __restrict__ a, const float* __restrict__ w,
+                                                       const float* __restrict__ b, float* __restrict__ out, int n, int H, int W,
+                                                       int C, int Co) {
+    extern __shared__ uint2 bfrag[];  // [9][C / 32][2][32]
+    const int CB = C >> 5;
+    for (int i = threadIdx.x; i < 9 * CB * 64; i += blockDim.x) {
+        const int lane = i & 31, s = (i >> 5) & 1, cb = (i >> 6) % CB, tap = (i >> 6) / CB;
+        const int g = lane >> 2, t = lane & 3;
+        const int ch0 = cb * 32 + 8 * t + 4 * s;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (g < Co)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = w[((long long)(g * C + ch0 + j)) * 9 + tap];  // [Co, C, 3, 3]
+        bfrag[i] = pack4_bf16(v[0], v[1], v[2], v[3]);
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int xsegs = (W + 31) / 32, ysegs = (H + 3) / 4;
+    const int ntiles = n * xsegs * ysegs;
+    const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {  // the fragment table above is built once per block
+    const int bx = tile % xsegs, by = (tile / xsegs) % ysegs, img = tile / (xsegs * ysegs);
+    const int y0 = by * 4 + (warp >> 1), xb = bx * 32 + (warp & 1) * 16;
+    if (y0 >= H || xb >= W) continue;
+    float d[4] = {0.f, 0.f, 0.f, 0.f};
     for (int ky = 0; ky < 3; ++ky) {
         const int yy = y0 + ky - 1;
-        if (yy < 0 || yy >= H) continue;
-        for (int kx = 0; kx < 3; ++kx) {
-            const int xx = x0 + kx - 1;
-            if (xx < 0 || xx >= W) continue;
-            const uint4* src = reinterpret_cast<const uint4*>(a + ((img * H + yy) * W + xx) * C);
-            const float4* wt = reinterpret_cast<const float4*>(wsm + (ky * 3 + kx) * C * 4);
-            for (int c8 = 0; c8 < C / 8; ++c8) {
-                const uint4 v = __ldg(src + c8);
-                const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+        if (yy < 0 || yy >= H) continue;  // warp-uniform
+        const bf16* rowp = a + ((long long)(img * H + yy) * W) * C + 8 * t;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const float lo = __uint_as_float(u[q] << 16), hi = __uint_as_float(u[q] & 0xffff0000u);
-                    const float4 w0 = wt[c8 * 8 + 2 * q], w1 = wt[c8 * 8 + 2 * q + 1];
-                    acc[0] = fmaf(lo, w0.x, fmaf(hi, w1.x, acc[0]));
-                    acc[1] = fmaf(lo, w0.y, fmaf(hi, w1.y, acc[1]));
-                    acc[2] = fmaf(lo, w0.z, fmaf(hi, w1.z, acc[2]));
-                    acc[3] = fmaf(lo, w0.w, fmaf(hi, w1.w, acc[3]));
-                }
+        for (int kx = 0; kx < 3; ++kx) {
+            const int xa = xb + g + kx - 1, xc = xa + 8;
+            const bool oka = xa >= 0 && xa < W, okc = xc >= 0 && xc < W;
+            const uint4* pa = reinterpret_cast<const uint4*>(rowp + (long long)xa * C);
+            const uint4* pc = reinterpret_cast<const uint4*>(rowp + (long long)xc * C);
+            const uint2* bf = bfrag + ((ky * 3 + kx) * CB) * 64 + lane;
+#pragma unroll 4
+            for (int cb = 0; cb < CB; ++cb) {
+                const uint4 va = oka ? __ldg(pa + cb * 4) : zero4, vc = okc ? __ldg(pc + cb * 4) : zero4;
+                const uint2 b0 = bf[cb * 64], b1 = bf[cb * 64 + 32];
+                asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                             : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                             : "r"(va.x), "r"(vc.x), "r"(va.y), "r"(vc.y), "r"(b0.x), "r"(b0.y));
+                asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                             : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                             : "r"(va.z), "r"(vc.z), "r"(va.w), "r"(vc.w), "r"(b1.x), "r"(b1.y));
             }
         }
     }
-    for (int o = 0; o < Co; ++o) out[((img * Co + o) * H + y0) * W + x0] = acc[o] + __ldg(b + o);
+    // d0, d1: pixel g, output channels 2t, 2t + 1;  d2, d3: pixel g + 8
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int o = 2 * t + j;
+        if (o < Co) {
+            const float bias = __ldg(b + o);
+            float* op = out + ((long long)(img * Co + o) * H + y0) * W;
+            if (xb + g < W) op[xb + g] = d[j] + bias;
+            if (xb + g + 8 < W) op[xb + g + 8] = d[2 + j] + bias;
+        }
+    }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------- attention helpers
@@ -537,9 +590,8 @@ struct pdm_vae {
         check_launch("gn_stats");
         gn_finalize_kernel<<<ceil_div(n * GN_GROUPS, 128), 128, 0, s>>>(b.part, b.mr, n, nblk, (double)hw * (C / GN_GROUPS), 1e-6f);
         check_launch("gn_finalize");
-        const long long total4 = (long long)n * hw * C / 4;
-        const int grid = (int)std::min<long long>(ceil_div_ll(total4, 256), 148 * 16);
-        gn_apply_kernel<<<grid, 256, 0, s>>>(x, b.mr, gw, gb, out, total4, hw, C, act ? 1 : 0);
+        const int ppb = 8 * (256 / (C / 4));  // 8 pixels per thread
+        gn_apply_kernel<<<dim3(ceil_div(hw, ppb), n), 256, 0, s>>>(x, b.mr, gw, gb, out, hw, C, act ? 1 : 0, ppb);
         check_launch("gn_apply");
     }
     // out32 (+= if accumulate) = conv3x3(a16) + bias
@@ -562,9 +614,8 @@ struct pdm_vae {
         gemm_tc_bf16(g, s);
     }
     void to_bf16(const float* x, bf16* out, int n, int H, int W, int C, bool upsample, cudaStream_t s) {
-        const long long total4 = (long long)n * H * W * C / 4 * (upsample ? 4 : 1);
-        const int grid = (int)std::min<long long>(ceil_div_ll(total4, 256), 148 * 16);
-        convert_up_kernel<<<grid, 256, 0, s>>>(x, out, total4, H, W, C, upsample ? 1 : 0);
+        const int Ho = upsample ? 2 * H : H, Wo = upsample ? 2 * W : W;
+        convert_up_kernel<<<dim3(n * Ho, ceil_div(Wo * (C / 4), 256)), 256, 0, s>>>(x, out, H, W, C, upsample ? 1 : 0);
         check_launch("convert_up");
     }
     // x (b.X, [n, hw, Cin]) -> b.X ([n, hw, Cout])        (libs/autoencoder.py:114-134)
@@ -619,8 +670,7 @@ struct pdm_vae {
         int H = h0, W = h0;
         const int C0 = ch_at(nlev - 1);
         {
-            const long long total = (long long)n * H * W * (C0 / 4);
-            conv_in_kernel<4><<<(unsigned)ceil_div_ll(total, 128), 128, 0, s>>>(
+            conv_in_kernel<4><<<(unsigned)(n * H * ceil_div(W, CIN_PX)), 128, 0, s>>>(
                 z, params.at("post_quant_conv.weight").d32, params.at("post_quant_conv.bias").d32,
                 params.at("decoder.conv_in.weight").d32, params.at("decoder.conv_in.bias").d32, b.X, n, H, W, C0,
                 1.f / cfg.scale_factor);
@@ -642,8 +692,8 @@ struct pdm_vae {
         const int Cl = ch_at(0);
         group_norm(b, b.X, params.at("decoder.norm_out.weight").d32, params.at("decoder.norm_out.bias").d32, b.A16, n, H * W, Cl,
                    true, s);
-        PDM_REQUIRE(cfg.out_ch <= 4 && Cl % 8 == 0, "VAE: out_ch <= 4");
-        conv_out_kernel<<<(unsigned)ceil_div_ll((long long)n * H * W, 128), 128, 9 * Cl * 4 * sizeof(float), s>>>(
+        PDM_REQUIRE(cfg.out_ch <= 4 && Cl % 32 == 0, "VAE: out_ch <= 4, last level channels a multiple of 32");
+        conv_out_kernel<<<(unsigned)std::min(n * ceil_div(H, 4) * ceil_div(W, 32), 148 * 8), 256, 9 * (Cl / 32) * 64 * sizeof(uint2), s>>>(
             b.A16, params.at("decoder.conv_out.weight").d32, params.at("decoder.conv_out.bias").d32, out, n, H, W, Cl, cfg.out_ch);
         check_launch("vae_conv_out");
     }
