@@ -127,6 +127,10 @@ struct GemmProblem {
     // (Lr = conv_N * conv_H * conv_W, nb = 1), K1 = 9 * conv_C with k = (ky * 3 + kx) * conv_C + c, W16 = [N, 9 * conv_C].
     // The A tile of tap (ky, kx) is ONE shifted TMA box of the activation; the border comes from the out-of-bounds zero fill.
     int conv_N = 0, conv_H = 0, conv_W = 0, conv_C = 0;
+    // conv_up = 1 + 2 a + b (0 = off): phase (a, b) of "nearest 2x upsample -> 3x3 convolution" as a 2x2 convolution over the
+    // LOW-resolution activation: K1 = 4 * conv_C with k = (dy * 2 + dx) * conv_C + c reading source pixel (y + dy + a - 1,
+    // x + dx + b - 1); row (n, y, x) of the result is written to row (n, 2 y + a, 2 x + b) of out32 [conv_N, 2 H, 2 W, N].
+    int conv_up = 0;
 };
 
 void gemm_simt_f32(const GemmProblem& p, cudaStream_t s);

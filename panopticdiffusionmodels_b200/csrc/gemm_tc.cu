@@ -46,7 +46,7 @@ constexpr int BN = 256, BK = 64;
 constexpr int A_BYTES = BM * BK * 2;
 constexpr int SCR_STRIDE = 36;  // 32-bit words per scratch row: 128 B payload + 16 B pad (16 B aligned, conflict-free)
 enum { EPI_F32 = 0, EPI_PACK = 1, EPI_LN = 2, EPI_LN_GELU = 3, EPI_F32_EMIT = 4, EPI_LN_GELU_W16 = 5, EPI_F32_TMA = 6,
-       EPI_F32_EMIT_RB = 7 };  // _RB: EMIT + per-row bias table (the patch-embed GEMM: positional rows, bf16 copies, row sums)
+       EPI_F32_EMIT_RB = 7, EPI_F32_UP = 8 };  // _RB: EMIT + per-row bias table (the patch-embed GEMM: positional rows, bf16 copies, row sums)
 constexpr int TMA_WARP_BYTES = 3 * 4096 + 2048;  // EPI_F32_TMA: 3 fp32 [32 x 32] staging tiles + 1 bf16 [32 x 32] tile per warp
 
 // Epilogue geometry per form.  Each epilogue warp covers one TMEM lane quarter x WCOLS accumulator columns.  The
@@ -115,6 +115,8 @@ struct TcParams {
     // implicit-GEMM 3x3 convolution (conv_hw > 0): A through a 4-D map [C, W, H, N]
     int conv_hw, conv_W, conv_H, conv_kbc;  // pixels per image, width, height, k-blocks per tap (C / 64)
     int conv_ht, conv_wt;                   // tile = conv_ht rows x conv_wt pixels (128 consecutive output pixels)
+    int conv_kw, conv_ox, conv_oy;          // taps per kernel row (3, or 2 for an upsample phase), source offset of tap (0, 0)
+    int up_a, up_b;                         // EPI_F32_UP: output row (n, 2 y + up_a, 2 x + up_b)
 };
 
 // GELU(erf) for the bf16 path (libs/timm.py:101 -> nn.GELU()).  x.Phi(x) = 0.5 x (1 + tanh(x (a + b x^2 + c x^4)))
@@ -340,14 +342,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
                     const int ka = (kb < p.KB1 ? kb : kb - p.KB1) * BK;
                     if (p.conv_hw) {
                         const int tap = kb / p.conv_kbc, cb = kb - tap * p.conv_kbc;
-                        const int ky = tap / 3, kx = tap - 3 * ky;
+                        const int ky = tap / p.conv_kw, kx = tap - p.conv_kw * ky;
                         if (ptx::elect_one()) {
                             if (rank == 0) ptx::mbar_expect_tx(&full[stage], NCTA * STAGE_BYTES);
                             if (NCTA == 2) {
-                                ptx::tma_load_4d_2sm(&tmA1, &full[stage], sa, cb * BK, cw0 + kx - 1, ch0 + ky - 1, cn);
+                                ptx::tma_load_4d_2sm(&tmA1, &full[stage], sa, cb * BK, cw0 + kx + p.conv_ox, ch0 + ky + p.conv_oy, cn);
                                 ptx::tma_load_3d_2sm(&tmB, &full[stage], sb, kb * BK, n0, 0);
                             } else {
-                                ptx::tma_load_4d(&tmA1, &full[stage], sa, cb * BK, cw0 + kx - 1, ch0 + ky - 1, cn);
+                                ptx::tma_load_4d(&tmA1, &full[stage], sa, cb * BK, cw0 + kx + p.conv_ox, ch0 + ky + p.conv_oy, cn);
                                 ptx::tma_load_3d(&tmB, &full[stage], sb, kb * BK, n0, 0);
                             }
                         }
@@ -420,7 +422,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         const int half = ew >> 2;  // which WCOLS-column slice of the tile
         uint32_t* scr = reinterpret_cast<uint32_t*>(scr_base + ew * SCR_BYTES);
         float* sbias = reinterpret_cast<float*>(scr + (G::TMA ? TMA_WARP_BYTES / 4 : (G::PTMA ? 1024 : 32 * SCR_STRIDE)));  // [WCOLS]
-        constexpr bool packed = EPI != EPI_F32 && EPI != EPI_F32_EMIT && EPI != EPI_F32_TMA && EPI != EPI_F32_EMIT_RB;
+        constexpr bool packed = EPI != EPI_F32 && EPI != EPI_F32_EMIT && EPI != EPI_F32_TMA && EPI != EPI_F32_EMIT_RB && EPI != EPI_F32_UP;
+        constexpr bool UP = EPI == EPI_F32_UP;  // plain fp32 form whose rows scatter into a 2x upsampled NHWC tensor
         constexpr bool EMIT = EPI == EPI_F32_EMIT || EPI == EPI_F32_EMIT_RB;
         constexpr bool RB = EPI == EPI_F32 || EPI == EPI_F32_EMIT_RB;  // forms that honour p.rowbias
         constexpr bool LN = G::LN;
@@ -781,7 +784,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
                             // (two chunks ahead, and an L2 bulk prefetch of the next tile's slice, both measured SLOWER)
                             if (next_ok && row_ok) res[ps] = *reinterpret_cast<const float4*>(po + 32);
                         }
-                        if (col_ok && row_ok) {
+                        if constexpr (UP) {
+                            if (col_ok && row_ok) {
+                                const int t = trow0 + r;
+                                const int gy = t / p.conv_W, gx = t - gy * p.conv_W;  // gy = n * H + y
+                                *reinterpret_cast<float4*>(p.out32 + ((long long)(2 * gy + p.up_a) * (2 * p.conv_W) + 2 * gx + p.up_b) * p.N + col) = a;
+                            }
+                        } else if (col_ok && row_ok) {
                             *reinterpret_cast<float4*>(po) = a;
                             if (pob) *reinterpret_cast<float4*>(pob) = a;
                             if (ph) *reinterpret_cast<uint2*>(ph) = make_uint2(pack2(a.x, a.y), pack2(a.z, a.w));
@@ -907,6 +916,11 @@ void launch(const GemmProblem& g, cudaStream_t s) {
     }
     p.rowbias = g.rowbias;
     p.conv_hw = p.conv_W = p.conv_H = p.conv_kbc = p.conv_ht = p.conv_wt = 0;
+    p.conv_kw = 3; p.conv_ox = p.conv_oy = -1; p.up_a = p.up_b = 0;
+    if (g.conv_up) {
+        p.up_a = (g.conv_up - 1) >> 1; p.up_b = (g.conv_up - 1) & 1;
+        p.conv_kw = 2; p.conv_oy = p.up_a - 1; p.conv_ox = p.up_b - 1;
+    }
     if (g.conv_H > 0) {
         p.conv_hw = g.conv_H * g.conv_W;
         p.conv_W = g.conv_W;
@@ -1040,8 +1054,12 @@ void gemm_tc_bf16(const GemmProblem& g, cudaStream_t s) {
     PDM_REQUIRE(!g.statsb || g.stats, "gemm_tc: statsb needs stats");
     if (g.conv_H > 0) {
         const int hw = g.conv_H * g.conv_W;
-        PDM_REQUIRE(g.nb == 1 && !g.A2 && g.conv_C % BK == 0 && g.K1 == 9 * g.conv_C && g.Lr == g.conv_N * hw,
-                    "gemm_tc(conv): K1 = 9 C with C % 64 == 0, rows = N H W");
+        PDM_REQUIRE(g.conv_up >= 0 && g.conv_up <= 4, "gemm_tc(conv): conv_up is 0 or 1 + 2 a + b");
+        PDM_REQUIRE(g.nb == 1 && !g.A2 && g.conv_C % BK == 0 && g.K1 == (g.conv_up ? 4 : 9) * g.conv_C && g.Lr == g.conv_N * hw,
+                    "gemm_tc(conv): K1 = 9 C (4 C for an upsample phase) with C % 64 == 0, rows = N H W");
+        PDM_REQUIRE(!g.conv_up || (g.out32 && !g.resid && !g.out32b && !g.out2 && !g.out2b && !g.stats && !g.gelu && !g.rowbias && !ln &&
+                                   g.N % 4 == 0),
+                    "gemm_tc(conv): an upsample phase is a plain fp32-output GEMM");
         PDM_REQUIRE(hw % BM == 0 && (g.conv_W >= BM ? g.conv_W % BM == 0 : (BM % g.conv_W == 0 && g.conv_H % (BM / g.conv_W) == 0)),
                     "gemm_tc(conv): a 128-pixel tile must be whole image rows (or a row segment) of one image");
     }
@@ -1053,6 +1071,10 @@ void gemm_tc_bf16(const GemmProblem& g, cudaStream_t s) {
     static const bool tma_noresid = getenv("PDM_GEMM_TMA_NORESID") != nullptr;
     const bool tma_ok = tma_epi && g.out32 && (g.resid || tma_noresid) && !g.gelu && g.N % 32 == 0 && K_total(g) <= tma_maxk &&
                         (!g.out2b || (g.out2b_row0 == 0 && g.out2b_mod == 0));
+    if (g.conv_up) {
+        if (one_cta) launch<1, EPI_F32_UP>(g, s); else launch<2, EPI_F32_UP>(g, s);
+        return;
+    }
     const int epi = g.out32 ? (tma_ok ? EPI_F32_TMA : ((g.stats || g.out2b) ? (g.rowbias ? EPI_F32_EMIT_RB : EPI_F32_EMIT) : EPI_F32))
                             : (ln ? (g.gelu ? (g.K1 <= 512 ? EPI_LN_GELU_W16 : EPI_LN_GELU) : EPI_LN) : EPI_PACK);
     if (one_cta) {

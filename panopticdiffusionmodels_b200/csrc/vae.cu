@@ -47,11 +47,17 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__
     float s1 = 0.f, s2 = 0.f;
     if (prow < pstep) {
         const float4* base = reinterpret_cast<const float4*>(x + ((long long)n * hw) * C) + col;
-        for (int p = p0 + prow; p < p1; p += pstep) {
-            const float4 v = __ldg(base + (long long)p * c4n);
+        auto acc = [&](const float4 v) {
             s1 += (v.x + v.y) + (v.z + v.w);
             s2 = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, s2))));
+        };
+        int p = p0 + prow;
+        for (; p + 3 * pstep < p1; p += 4 * pstep) {  // four 16-byte loads in flight; the summation order stays fixed
+            const float4 v0 = __ldg(base + (long long)p * c4n), v1 = __ldg(base + (long long)(p + pstep) * c4n);
+            const float4 v2 = __ldg(base + (long long)(p + 2 * pstep) * c4n), v3 = __ldg(base + (long long)(p + 3 * pstep) * c4n);
+            acc(v0); acc(v1); acc(v2); acc(v3);
         }
+        for (; p < p1; p += pstep) acc(__ldg(base + (long long)p * c4n));
     }
     ts[threadIdx.x][0] = s1;
     ts[threadIdx.x][1] = s2;
@@ -123,19 +129,29 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__
     }
     for (; p < p1; p += pstep) one(__ldg(src + (long long)p * c4n), p);
 }
-// fp32 NHWC -> bf16 NHWC, optionally through a nearest-neighbour 2x upsample (F.interpolate(scale_factor=2, 'nearest')).
-// Grid (output rows n * Ho, ceil(Wo * C/4 / 256)): 32-bit index arithmetic only.
+// fp32 NHWC -> bf16 NHWC, optionally through a nearest-neighbour 2x upsample (F.interpolate(scale_factor=2, 'nearest')):
+// a thread reads one float4 of a SOURCE pixel and writes it to the 1 (or 2 x 2) output pixels it maps to.
+// Grid (source rows n * H, ceil(W * C/4 / 256)): 32-bit index arithmetic only.
 __global__ void __launch_bounds__(256) convert_up_kernel(const float* __restrict__ x, bf16* __restrict__ out, int H, int W, int C,
                                                          int up) {
     const int c4n = C >> 2;
-    const int Ho = up ? 2 * H : H, Wo = up ? 2 * W : W;
-    const int e = blockIdx.y * blockDim.x + threadIdx.x;  // (wo, col) within the output row
-    if (e >= Wo * c4n) return;
-    const int wo = e / c4n, col = e - wo * c4n;
-    const int row = blockIdx.x, n = row / Ho, ho = row - n * Ho;
-    const int h = up ? ho >> 1 : ho, w = up ? wo >> 1 : wo;
-    const float4 v = __ldg(reinterpret_cast<const float4*>(x) + ((long long)(n * H + h) * W + w) * c4n + col);
-    reinterpret_cast<uint2*>(out)[(long long)row * Wo * c4n + e] = pack4_bf16(v.x, v.y, v.z, v.w);
+    const int e = blockIdx.y * blockDim.x + threadIdx.x;  // (w, col) within the source row
+    if (e >= W * c4n) return;
+    const int w = e / c4n, col = e - w * c4n;
+    const int row = blockIdx.x;  // n * H + h
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x) + (long long)row * W * c4n + e);
+    const uint2 o = pack4_bf16(v.x, v.y, v.z, v.w);
+    uint2* dst = reinterpret_cast<uint2*>(out);
+    if (!up) {
+        dst[(long long)row * W * c4n + e] = o;
+    } else {
+        const int Wo = 2 * W;
+        const long long r0 = ((long long)row * 2 * Wo + 2 * w) * c4n + col;  // output row 2 (n H + h) = n Ho + 2 h
+        dst[r0] = o;
+        dst[r0 + c4n] = o;
+        dst[r0 + (long long)Wo * c4n] = o;
+        dst[r0 + (long long)Wo * c4n + c4n] = o;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------- the two narrow convolutions
@@ -299,6 +315,28 @@ __global__ void repack_conv3_kernel(const float* __restrict__ w, bf16* __restric
     const int o = (int)(i / ((long long)Cin * 9));
     out[i] = __float2bfloat16(w[((long long)o * Cin + c) * 9 + tap]);
 }
+// "nearest 2x upsample -> 3x3 convolution" = four 2x2 convolutions over the low-resolution input, one per output phase
+// (a, b) = (row, column) parity: output pixel (2y + a, 2x + b) only ever sees source pixels (y + dy + a - 1, x + dx + b - 1),
+// dy, dx in {0, 1}, and the 3x3 taps that land on the same source pixel add up (summed in fp32, rounded to bf16 once):
+//   a = 0: dy = 0 <- ky {0},     dy = 1 <- ky {1, 2}          a = 1: dy = 0 <- ky {0, 1},  dy = 1 <- ky {2}      (same for b / kx)
+// 16 instead of 36 multiply-adds per output pixel and channel pair, and the 4x larger upsampled operand is never written.
+// out: [phase = 2a + b][Cout][dy][dx][Cin] bf16.
+__global__ void repack_up_phases_kernel(const float* __restrict__ w, bf16* __restrict__ out, int Cout, int Cin) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long per = (long long)Cout * 4 * Cin;
+    if (i >= 4 * per) return;
+    const int ph = (int)(i / per), a = ph >> 1, b = ph & 1;
+    const long long j = i - ph * per;
+    const int c = (int)(j % Cin), tap = (int)((j / Cin) % 4), o = (int)(j / (4LL * Cin));
+    const int dy = tap >> 1, dx = tap & 1;
+    const int ky0 = a == 0 ? (dy == 0 ? 0 : 1) : (dy == 0 ? 0 : 2), ky1 = a == 0 ? (dy == 0 ? 0 : 2) : (dy == 0 ? 1 : 2);
+    const int kx0 = b == 0 ? (dx == 0 ? 0 : 1) : (dx == 0 ? 0 : 2), kx1 = b == 0 ? (dx == 0 ? 0 : 2) : (dx == 0 ? 1 : 2);
+    const float* wc = w + ((long long)o * Cin + c) * 9;  // [Cout, Cin, 3, 3]
+    float acc = 0.f;
+    for (int ky = ky0; ky <= ky1; ++ky)
+        for (int kx = kx0; kx <= kx1; ++kx) acc += wc[ky * 3 + kx];
+    out[i] = __float2bfloat16(acc);
+}
 // b_out[o] = b_o[o] + sum_c W_o[o, c] * b_v[c]   (v's bias commutes with the softmax: rows of P sum to one)
 __global__ void fold_v_bias_kernel(const float* __restrict__ Wo, const float* __restrict__ bo, const float* __restrict__ bv,
                                    float* __restrict__ out, int C) {
@@ -317,6 +355,7 @@ struct VParam {
 };
 struct Conv3 {  // 3x3 convolution as implicit GEMM
     bf16* w16 = nullptr;  // [Cout][9][Cin]
+    bf16* wup = nullptr;  // Upsample convolutions only: [4 phases][Cout][2][2][Cin] (repack_up_phases_kernel)
     const float* b = nullptr;
     int Cin = 0, Cout = 0;
 };
@@ -508,7 +547,13 @@ struct pdm_vae {
             }
             if (lev != 0) {
                 up[lev].has_up = true;
-                up[lev].up = conv3("decoder.up." + std::to_string(lev) + ".upsample.conv.", block_in, block_in, s);
+                const std::string pre = "decoder.up." + std::to_string(lev) + ".upsample.conv.";
+                up[lev].up = conv3(pre, block_in, block_in, s);
+                const long long nw = 16LL * block_in * block_in;
+                up[lev].up.wup = dev_alloc<bf16>((size_t)nw);
+                repack_up_phases_kernel<<<(unsigned)ceil_div_ll(nw, 256), 256, 0, s>>>(params.at(pre + "weight").d32, up[lev].up.wup,
+                                                                                       block_in, block_in);
+                check_launch("repack_up_phases");
             }
         }
         PDM_CHECK_CUDA(cudaStreamSynchronize(s));
@@ -614,8 +659,7 @@ struct pdm_vae {
         gemm_tc_bf16(g, s);
     }
     void to_bf16(const float* x, bf16* out, int n, int H, int W, int C, bool upsample, cudaStream_t s) {
-        const int Ho = upsample ? 2 * H : H, Wo = upsample ? 2 * W : W;
-        convert_up_kernel<<<dim3(n * Ho, ceil_div(Wo * (C / 4), 256)), 256, 0, s>>>(x, out, H, W, C, upsample ? 1 : 0);
+        convert_up_kernel<<<dim3(n * H, ceil_div(W * (C / 4), 256)), 256, 0, s>>>(x, out, H, W, C, upsample ? 1 : 0);
         check_launch("convert_up");
     }
     // x (b.X, [n, hw, Cin]) -> b.X ([n, hw, Cout])        (libs/autoencoder.py:114-134)
@@ -683,9 +727,17 @@ struct pdm_vae {
             for (auto& r : up[lev].blocks) res_block(r, b, n, H, W, s);
             if (up[lev].has_up) {  // nearest 2x + 3x3 conv (libs/autoencoder.py:46-50)
                 const int C = up[lev].up.Cin;
-                to_bf16(b.X, b.A16, n, H, W, C, true, s);
+                to_bf16(b.X, b.A16, n, H, W, C, false, s);
+                for (int ph = 0; ph < 4; ++ph) {  // four 2x2 phase convolutions over the low-resolution operand
+                    GemmProblem g;
+                    g.A1 = b.A16; g.K1 = 4 * C; g.W16 = up[lev].up.wup + (size_t)ph * up[lev].up.Cout * 4 * C;
+                    g.bias = up[lev].up.b; g.N = up[lev].up.Cout;
+                    g.nb = 1; g.Lr = n * H * W;
+                    g.out32 = b.X2;
+                    g.conv_N = n; g.conv_H = H; g.conv_W = W; g.conv_C = C; g.conv_up = 1 + ph;
+                    gemm_tc_bf16(g, s);
+                }
                 H *= 2; W *= 2;
-                conv3_gemm(up[lev].up, b.A16, b.X2, false, n, H, W, s);
                 std::swap(b.X, b.X2);
             }
         }
