@@ -131,6 +131,11 @@ struct GemmProblem {
     // LOW-resolution activation: K1 = 4 * conv_C with k = (dy * 2 + dx) * conv_C + c reading source pixel (y + dy + a - 1,
     // x + dx + b - 1); row (n, y, x) of the result is written to row (n, 2 y + a, 2 x + b) of out32 [conv_N, 2 H, 2 W, N].
     int conv_up = 0;
+    // GroupNorm statistics of the OUTPUT (fp32 plain / += / upsample-phase forms, nb = 1, rows = pixels of whole images):
+    // per (image, 32-row slab, group) partial (sum, sum of squares) in a fixed order -> gn_part[img][blk][32 groups][2],
+    // blk = slab_in_image * gn_stride + gn_slot0, gn_nblk slabs-times-stride per image.  N = 32 * channels-per-group.
+    float* gn_part = nullptr;
+    int gn_hw = 0, gn_stride = 1, gn_slot0 = 0;
 };
 
 void gemm_simt_f32(const GemmProblem& p, cudaStream_t s);

@@ -46,7 +46,7 @@ constexpr int BN = 256, BK = 64;
 constexpr int A_BYTES = BM * BK * 2;
 constexpr int SCR_STRIDE = 36;  // 32-bit words per scratch row: 128 B payload + 16 B pad (16 B aligned, conflict-free)
 enum { EPI_F32 = 0, EPI_PACK = 1, EPI_LN = 2, EPI_LN_GELU = 3, EPI_F32_EMIT = 4, EPI_LN_GELU_W16 = 5, EPI_F32_TMA = 6,
-       EPI_F32_EMIT_RB = 7, EPI_F32_UP = 8 };  // _RB: EMIT + per-row bias table (the patch-embed GEMM: positional rows, bf16 copies, row sums)
+       EPI_F32_EMIT_RB = 7, EPI_F32_UP = 8, EPI_F32_GN = 9 };  // _RB: EMIT + per-row bias table (the patch-embed GEMM: positional rows, bf16 copies, row sums)
 constexpr int TMA_WARP_BYTES = 3 * 4096 + 2048;  // EPI_F32_TMA: 3 fp32 [32 x 32] staging tiles + 1 bf16 [32 x 32] tile per warp
 
 // Epilogue geometry per form.  Each epilogue warp covers one TMEM lane quarter x WCOLS accumulator columns.  The
@@ -117,6 +117,9 @@ struct TcParams {
     int conv_ht, conv_wt;                   // tile = conv_ht rows x conv_wt pixels (128 consecutive output pixels)
     int conv_kw, conv_ox, conv_oy;          // taps per kernel row (3, or 2 for an upsample phase), source offset of tap (0, 0)
     int up_a, up_b;                         // EPI_F32_UP: output row (n, 2 y + up_a, 2 x + up_b)
+    // EPI_F32_GN / EPI_F32_UP: GroupNorm partial sums of the output (see GemmProblem::gn_part)
+    float* gn_part;
+    int gn_cpg, gn_tpi, gn_nblk, gn_stride, gn_slot0;  // channels per group, 128-row tiles per image, partial slots per image
 };
 
 // GELU(erf) for the bf16 path (libs/timm.py:101 -> nn.GELU()).  x.Phi(x) = 0.5 x (1 + tanh(x (a + b x^2 + c x^4)))
@@ -422,8 +425,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         const int half = ew >> 2;  // which WCOLS-column slice of the tile
         uint32_t* scr = reinterpret_cast<uint32_t*>(scr_base + ew * SCR_BYTES);
         float* sbias = reinterpret_cast<float*>(scr + (G::TMA ? TMA_WARP_BYTES / 4 : (G::PTMA ? 1024 : 32 * SCR_STRIDE)));  // [WCOLS]
-        constexpr bool packed = EPI != EPI_F32 && EPI != EPI_F32_EMIT && EPI != EPI_F32_TMA && EPI != EPI_F32_EMIT_RB && EPI != EPI_F32_UP;
+        constexpr bool packed = EPI != EPI_F32 && EPI != EPI_F32_EMIT && EPI != EPI_F32_TMA && EPI != EPI_F32_EMIT_RB && EPI != EPI_F32_UP &&
+                                EPI != EPI_F32_GN;
         constexpr bool UP = EPI == EPI_F32_UP;  // plain fp32 form whose rows scatter into a 2x upsampled NHWC tensor
+        constexpr bool GN = EPI == EPI_F32_GN || EPI == EPI_F32_UP;  // forms that can emit GroupNorm partial sums (p.gn_part)
         constexpr bool EMIT = EPI == EPI_F32_EMIT || EPI == EPI_F32_EMIT_RB;
         constexpr bool RB = EPI == EPI_F32 || EPI == EPI_F32_EMIT_RB;  // forms that honour p.rowbias
         constexpr bool LN = G::LN;
@@ -763,6 +768,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
                     float* pob = o32b ? o32b + 32 * chunk : nullptr;
                     bf16* ph = o16 ? o16 + 32 * chunk : nullptr;
                     bf16* phb = o16b ? o16b + 32 * chunk : nullptr;
+                    float g1 = 0.f, g2 = 0.f;  // GN forms: this lane's 8 rows x 4 columns of the chunk
 #pragma unroll
                     for (int ps = 0; ps < 8; ++ps) {
                         const int r = ps * 4 + rsub;
@@ -783,6 +789,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
                             // software pipeline: fetch the same row of the NEXT chunk into the slot just consumed
                             // (two chunks ahead, and an L2 bulk prefetch of the next tile's slice, both measured SLOWER)
                             if (next_ok && row_ok) res[ps] = *reinterpret_cast<const float4*>(po + 32);
+                        }
+                        if constexpr (GN) {
+                            if (col_ok && row_ok) {
+                                g1 += (a.x + a.y) + (a.z + a.w);
+                                g2 = fmaf(a.x, a.x, fmaf(a.y, a.y, fmaf(a.z, a.z, fmaf(a.w, a.w, g2))));
+                            }
                         }
                         if constexpr (UP) {
                             if (col_ok && row_ok) {
@@ -805,6 +817,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
                         if (ph) ph += rstep;
                         if constexpr (EMIT) {
                             if (phb) phb += rstep;
+                        }
+                    }
+                    if constexpr (GN) {
+                        if (p.gn_part) {
+                            // fixed-order combine: the 4 row sub-lanes of a column quad, then the quads of one group
+                            g1 += __shfl_xor_sync(0xffffffffu, g1, 8);  g2 += __shfl_xor_sync(0xffffffffu, g2, 8);
+                            g1 += __shfl_xor_sync(0xffffffffu, g1, 16); g2 += __shfl_xor_sync(0xffffffffu, g2, 16);
+                            for (int o = 1; o * 4 < p.gn_cpg; o <<= 1) {
+                                g1 += __shfl_xor_sync(0xffffffffu, g1, o);
+                                g2 += __shfl_xor_sync(0xffffffffu, g2, o);
+                            }
+                            if (tile_ok && col_ok && rsub == 0 && (col % p.gn_cpg) == 0) {
+                                const int img = mt / p.gn_tpi, slab = (mt - img * p.gn_tpi) * 4 + q;
+                                const long long blk = (long long)img * p.gn_nblk + slab * p.gn_stride + p.gn_slot0;
+                                reinterpret_cast<float2*>(p.gn_part)[blk * 32 + col / p.gn_cpg] = make_float2(g1, g2);
+                            }
                         }
                     }
                     bb = bb_next;
@@ -917,6 +945,13 @@ void launch(const GemmProblem& g, cudaStream_t s) {
     p.rowbias = g.rowbias;
     p.conv_hw = p.conv_W = p.conv_H = p.conv_kbc = p.conv_ht = p.conv_wt = 0;
     p.conv_kw = 3; p.conv_ox = p.conv_oy = -1; p.up_a = p.up_b = 0;
+    p.gn_part = g.gn_part;
+    p.gn_cpg = p.gn_tpi = p.gn_nblk = 1; p.gn_stride = g.gn_stride; p.gn_slot0 = g.gn_slot0;
+    if (g.gn_part) {
+        p.gn_cpg = g.N / 32;
+        p.gn_tpi = g.gn_hw / BM;
+        p.gn_nblk = (g.gn_hw / 32) * g.gn_stride;
+    }
     if (g.conv_up) {
         p.up_a = (g.conv_up - 1) >> 1; p.up_b = (g.conv_up - 1) & 1;
         p.conv_kw = 2; p.conv_oy = p.up_a - 1; p.conv_ox = p.up_b - 1;
@@ -1063,6 +1098,10 @@ void gemm_tc_bf16(const GemmProblem& g, cudaStream_t s) {
         PDM_REQUIRE(hw % BM == 0 && (g.conv_W >= BM ? g.conv_W % BM == 0 : (BM % g.conv_W == 0 && g.conv_H % (BM / g.conv_W) == 0)),
                     "gemm_tc(conv): a 128-pixel tile must be whole image rows (or a row segment) of one image");
     }
+    PDM_REQUIRE(!g.gn_part || (g.out32 && g.nb == 1 && !g.out32b && !g.out2 && !g.out2b && !g.stats && !g.gelu && !g.rowbias && !ln &&
+                               g.N % 128 == 0 && g.N <= 1024 && g.gn_hw > 0 && g.gn_hw % BM == 0 && g.Lr % g.gn_hw == 0 &&
+                               g.gn_stride >= 1 && g.gn_slot0 >= 0 && g.gn_slot0 < g.gn_stride),
+                "gemm_tc: GroupNorm partial sums ride the plain fp32 forms (32 groups of >= 4 channels, whole images of 128-row tiles)");
     static const bool one_cta = getenv("PDM_GEMM_1CTA") != nullptr;
     // TMA-store epilogue: the HBM-bound read-modify-write GEMMs (proj, zero-conv: K <= 1024).  It leaves room for a 3-stage
     // operand ring only, so the tensor-bound K >= 2048 forms (fc2) and the skip GEMM keep the register-transpose epilogue.
@@ -1073,6 +1112,10 @@ void gemm_tc_bf16(const GemmProblem& g, cudaStream_t s) {
                         (!g.out2b || (g.out2b_row0 == 0 && g.out2b_mod == 0));
     if (g.conv_up) {
         if (one_cta) launch<1, EPI_F32_UP>(g, s); else launch<2, EPI_F32_UP>(g, s);
+        return;
+    }
+    if (g.gn_part) {
+        if (one_cta) launch<1, EPI_F32_GN>(g, s); else launch<2, EPI_F32_GN>(g, s);
         return;
     }
     const int epi = g.out32 ? (tma_ok ? EPI_F32_TMA : ((g.stats || g.out2b) ? (g.rowbias ? EPI_F32_EMIT_RB : EPI_F32_EMIT) : EPI_F32))

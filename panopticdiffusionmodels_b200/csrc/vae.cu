@@ -17,6 +17,7 @@
 // roles of weight and activation swapped produces directly; v's bias commutes with the softmax and is folded into
 // proj_out's).
 #include <cstring>
+#include <cstdlib>
 #include <map>
 #include <memory>
 #include <string>
@@ -76,22 +77,30 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__
         o[1] = a2;
     }
 }
-__global__ void gn_finalize_kernel(const float* __restrict__ part, float* __restrict__ mr, int n_images, int nblk, double count,
-                                   float eps) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per (image, group): lane-strided fp64 partial sums, then a fixed xor tree -- the same bits on every run
+__global__ void __launch_bounds__(128) gn_finalize_kernel(const float* __restrict__ part, float* __restrict__ mr, int n_images,
+                                                          int nblk, double count, float eps) {
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (i >= n_images * GN_GROUPS) return;
     const int n = i / GN_GROUPS, g = i - n * GN_GROUPS;
     double s1 = 0.0, s2 = 0.0;
-    for (int b = 0; b < nblk; ++b) {
-        const float* o = part + (((long long)n * nblk + b) * GN_GROUPS + g) * 2;
-        s1 += (double)o[0];
-        s2 += (double)o[1];
+    for (int b = lane; b < nblk; b += 32) {
+        const float2 o = __ldg(reinterpret_cast<const float2*>(part) + ((long long)n * nblk + b) * GN_GROUPS + g);
+        s1 += (double)o.x;
+        s2 += (double)o.y;
     }
-    const double mean = s1 / count;
-    double var = s2 / count - mean * mean;
-    if (var < 0.0) var = 0.0;
-    mr[2 * i] = (float)mean;
-    mr[2 * i + 1] = (float)(1.0 / sqrt(var + (double)eps));
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    if (lane == 0) {
+        const double mean = s1 / count;
+        double var = s2 / count - mean * mean;
+        if (var < 0.0) var = 0.0;
+        mr[2 * i] = (float)mean;
+        mr[2 * i + 1] = (float)(1.0 / sqrt(var + (double)eps));
+    }
 }
 __device__ __forceinline__ float swish(float v) { return __fdividef(v, 1.f + __expf(-v)); }
 __device__ __forceinline__ uint2 pack4_bf16(float y0, float y1, float y2, float y3) {
@@ -383,6 +392,8 @@ struct pdm_vae {
     std::map<std::string, VParam> params;
     std::vector<void*> owned;  // derived device buffers
     bool finalized = false;
+    // development switch: PDM_VAE_NO_FUSED_GN=1 keeps the stand-alone GroupNorm statistics pass for every tensor
+    bool fused_gn_stats = getenv("PDM_VAE_NO_FUSED_GN") == nullptr;
     // graph of layers
     ResBlock mid1, mid2;
     struct {
@@ -567,6 +578,9 @@ struct pdm_vae {
         bf16 *A16, *Q, *K, *VT, *P, *O;
         float* part;  // GroupNorm partial sums [n][slabs][32][2]
         float* mr;
+        // when the GEMM that produced a tensor also emitted its GroupNorm partial sums into `part` (GemmProblem::gn_part):
+        const float* stats_of = nullptr;
+        int stats_nblk = 0;
     };
     size_t max_act_elems(int n, int h0) const {  // largest [pixels, C] activation of the decoder for latent side h0
         size_t mx = 0;
@@ -605,7 +619,7 @@ struct pdm_vae {
         {
             int side = h0;
             for (int lev = nlev - 1; lev > 0; --lev) side *= 2;
-            b.part = (float*)take((size_t)n * ceil_div(side * side, GN_PPB) * GN_GROUPS * 2 * 4);
+            b.part = (float*)take((size_t)n * ceil_div(side * side, 32) * GN_GROUPS * 2 * 4);  // 32-row slabs of the GEMM epilogue
         }
         b.mr = (float*)take((size_t)n * GN_GROUPS * 2 * 4);
         *total = off + 256;
@@ -627,26 +641,41 @@ struct pdm_vae {
     }
 
     // ------------------------------------------------------------------ layers
-    void group_norm(const Buf& b, const float* x, const float* gw, const float* gb, bf16* out, int n, int hw, int C, bool act,
+    void group_norm(Buf& b, const float* x, const float* gw, const float* gb, bf16* out, int n, int hw, int C, bool act,
                     cudaStream_t s) {
         PDM_REQUIRE(C % (GN_GROUPS * 4) == 0 && C <= 1024, "GroupNorm: channels must be a multiple of 128 and <= 1024");
-        const int nblk = ceil_div(hw, GN_PPB);
-        gn_stats_kernel<<<dim3(nblk, n), 256, 0, s>>>(x, b.part, hw, C, GN_PPB);
-        check_launch("gn_stats");
-        gn_finalize_kernel<<<ceil_div(n * GN_GROUPS, 128), 128, 0, s>>>(b.part, b.mr, n, nblk, (double)hw * (C / GN_GROUPS), 1e-6f);
+        int nblk = b.stats_nblk;
+        if (b.stats_of != x) {  // producer without the fused statistics (conv_in, the attention's proj_out)
+            nblk = ceil_div(hw, GN_PPB);
+            gn_stats_kernel<<<dim3(nblk, n), 256, 0, s>>>(x, b.part, hw, C, GN_PPB);
+            check_launch("gn_stats");
+        }
+        b.stats_of = nullptr;
+        gn_finalize_kernel<<<ceil_div(n * GN_GROUPS, 4), 128, 0, s>>>(b.part, b.mr, n, nblk, (double)hw * (C / GN_GROUPS), 1e-6f);
         check_launch("gn_finalize");
         const int ppb = 8 * (256 / (C / 4));  // 8 pixels per thread
         gn_apply_kernel<<<dim3(ceil_div(hw, ppb), n), 256, 0, s>>>(x, b.mr, gw, gb, out, hw, C, act ? 1 : 0, ppb);
         check_launch("gn_apply");
     }
+    // the GEMM writing `out32` ([n, hw, N], whole images) also leaves the GroupNorm partial sums of its output in b.part
+    void emit_gn(GemmProblem& g, Buf& b, int hw, int stride = 1, int slot0 = 0) {
+        if (fused_gn_stats && g.N % (GN_GROUPS * 4) == 0 && g.N <= 1024 && hw % 128 == 0) {
+            g.gn_part = b.part; g.gn_hw = hw; g.gn_stride = stride; g.gn_slot0 = slot0;
+            b.stats_of = g.out32;
+            b.stats_nblk = (hw / 32) * stride;
+        } else if (b.stats_of == g.out32) {
+            b.stats_of = nullptr;
+        }
+    }
     // out32 (+= if accumulate) = conv3x3(a16) + bias
-    void conv3_gemm(const Conv3& c, const bf16* a16, float* out32, bool accumulate, int n, int H, int W, cudaStream_t s) {
+    void conv3_gemm(Buf& b, const Conv3& c, const bf16* a16, float* out32, bool accumulate, int n, int H, int W, cudaStream_t s) {
         GemmProblem g;
         g.A1 = a16; g.K1 = 9 * c.Cin; g.W16 = c.w16; g.bias = c.b; g.N = c.Cout;
         g.nb = 1; g.Lr = n * H * W;
         g.out32 = out32;
         if (accumulate) g.resid = out32;
         g.conv_N = n; g.conv_H = H; g.conv_W = W; g.conv_C = c.Cin;
+        emit_gn(g, b, H * W);  // every 3x3 convolution of the decoder feeds a GroupNorm (directly or through the residual sum)
         gemm_tc_bf16(g, s);
     }
     void conv1_gemm(const Conv1& c, const bf16* a16, const float* bias, float* out32, bool accumulate, bf16* out16, long long rows,
@@ -666,14 +695,14 @@ struct pdm_vae {
     void res_block(const ResBlock& r, Buf& b, int n, int H, int W, cudaStream_t s) {
         const int hw = H * W;
         group_norm(b, b.X, r.n1w, r.n1b, b.A16, n, hw, r.Cin, true, s);
-        conv3_gemm(r.c1, b.A16, b.H1, false, n, H, W, s);
+        conv3_gemm(b, r.c1, b.A16, b.H1, false, n, H, W, s);
         if (r.has_nin) {  // x = nin_shortcut(x): 1x1 on the raw stream
             to_bf16(b.X, b.A16, n, H, W, r.Cin, false, s);
             conv1_gemm(r.nin, b.A16, r.nin.b, b.X2, false, nullptr, (long long)n * hw, s);
             std::swap(b.X, b.X2);
         }
         group_norm(b, b.H1, r.n2w, r.n2b, b.A16, n, hw, r.Cout, true, s);
-        conv3_gemm(r.c2, b.A16, b.X, true, n, H, W, s);
+        conv3_gemm(b, r.c2, b.A16, b.X, true, n, H, W, s);
     }
     // x += proj_out(attention(norm(x)))                    (libs/autoencoder.py:171-195)
     void attn_block(Buf& b, int n, int H, int W, cudaStream_t s) {
@@ -704,6 +733,7 @@ struct pdm_vae {
             }
         }
         conv1_gemm(attn.o, b.O, attn.bo_folded, b.X, true, nullptr, (long long)n * L, s);
+        b.stats_of = nullptr;  // x changed through a form that does not emit GroupNorm sums
     }
 
     void decode(const float* z, float* out, int n, int h0, cudaStream_t s) {
@@ -735,6 +765,7 @@ struct pdm_vae {
                     g.nb = 1; g.Lr = n * H * W;
                     g.out32 = b.X2;
                     g.conv_N = n; g.conv_H = H; g.conv_W = W; g.conv_C = C; g.conv_up = 1 + ph;
+                    emit_gn(g, b, H * W, 4, ph);
                     gemm_tc_bf16(g, s);
                 }
                 H *= 2; W *= 2;
