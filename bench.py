@@ -267,6 +267,31 @@ def eager_torch_rate(kw, nfe, scale, dev, batch=32, evals=3):
 
 
 # ------------------------------------------------------------------------------------------------ our arm
+def vae_decode_rate(dev, batch=32, latent=32, iters=3):
+    """SURVEY 8(f) row 3, the step after the loop: latents -> 256 px images through `pdm_vae_decode` (SD decoder layout, random
+    weights, batch 32).  Outside every timed region of the headline metric, which excludes the VAE like the reference's
+    throughput does; reported so that the row has a driver-run number."""
+    import torch
+    from panopticdiffusionmodels_b200.libs.autoencoder import get_model
+    torch.manual_seed(0)
+    vae = get_model(None, 0.23010).to(dev)
+    z = torch.randn(batch, 4, latent, latent, device=dev)
+    vae.decode(z, max_batch=batch)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        img = vae.decode(z, max_batch=batch)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / iters
+    ok = bool(torch.isfinite(img).all())
+    del vae, z, img
+    torch.cuda.empty_cache()
+    return {"images_per_s": round(batch / ms * 1e3, 1), "ms_per_batch": round(ms, 2), "batch": batch, "image_px": latent * 8,
+            "finite": ok, "note": "pdm_vae_decode (csrc/vae.cu), random weights; not part of `value`"}
+
+
 def gemm_attn_flops(kw, B, nfe):
     """Algorithmic FLOPs of one step on one GPU, split into the GEMM kernels and the attention kernel."""
     D, depth, P = kw["embed_dim"], kw["depth"], (kw["img_size"] // 2) ** 2
@@ -462,6 +487,7 @@ def run_ours(a):
         line["torch_eager_b200"] = eager
         if extra:
             line["configs"] = extra
+            line["vae_decode"] = vae_decode_rate(dev) if world == 1 else None
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:

@@ -39,14 +39,15 @@ CUtensorMap make_tmap_bf16_nhwc(const void* ptr, long long C, long long W, long 
 namespace {
 
 constexpr int BM = 128;  // accumulator rows per CTA
-constexpr int BN = 256, BK = 64;
+constexpr int BK = 64;  // the N tile is per form: Geo<EPI>::BN (256; 128 for EPI_F32_GN128)
 #ifndef PDM_GEMM_LN_EPI_WARPS
 #define PDM_GEMM_LN_EPI_WARPS 16
 #endif
 constexpr int A_BYTES = BM * BK * 2;
 constexpr int SCR_STRIDE = 36;  // 32-bit words per scratch row: 128 B payload + 16 B pad (16 B aligned, conflict-free)
 enum { EPI_F32 = 0, EPI_PACK = 1, EPI_LN = 2, EPI_LN_GELU = 3, EPI_F32_EMIT = 4, EPI_LN_GELU_W16 = 5, EPI_F32_TMA = 6,
-       EPI_F32_EMIT_RB = 7, EPI_F32_UP = 8, EPI_F32_GN = 9 };  // _RB: EMIT + per-row bias table (the patch-embed GEMM: positional rows, bf16 copies, row sums)
+       EPI_F32_EMIT_RB = 7, EPI_F32_UP = 8, EPI_F32_GN = 9,
+       EPI_F32_GN128 = 10 };  // _GN128: the _GN form on a 256 x 128 pair tile (C_out = 128 convolutions: no half-empty MMAs)  // _RB: EMIT + per-row bias table (the patch-embed GEMM: positional rows, bf16 copies, row sums)
 constexpr int TMA_WARP_BYTES = 3 * 4096 + 2048;  // EPI_F32_TMA: 3 fp32 [32 x 32] staging tiles + 1 bf16 [32 x 32] tile per warp
 
 // Epilogue geometry per form.  Each epilogue warp covers one TMEM lane quarter x WCOLS accumulator columns.  The
@@ -59,7 +60,8 @@ struct Geo {
     static constexpr bool LN = EPI == EPI_LN || EPI == EPI_LN_GELU || EPI == EPI_LN_GELU_W16;
     static constexpr bool GELU = EPI == EPI_LN_GELU || EPI == EPI_LN_GELU_W16;
     static constexpr int EW = EPI == EPI_LN_GELU_W16 ? PDM_GEMM_LN_EPI_WARPS : 8;
-    static constexpr int WCOLS = 256 / (EW / 4);  // accumulator columns per epilogue warp
+    static constexpr int BN = EPI == EPI_F32_GN128 ? 128 : 256;  // accumulator tile width (columns of the CTA pair's tile)
+    static constexpr int WCOLS = BN / (EW / 4);  // accumulator columns per epilogue warp
     static constexpr int NBLK = WCOLS / 32;       // 32-column blocks per epilogue warp
     static constexpr int THREADS = 64 + EW * 32;
     static constexpr bool TMA = EPI == EPI_F32_TMA;
@@ -69,13 +71,13 @@ struct Geo {
     static constexpr int SCR_WORDS = TMA ? (TMA_WARP_BYTES + 1024) / 4 : (PTMA ? (4096 + 1024) / 4 : 32 * SCR_STRIDE + WCOLS);
     static constexpr int SCR_BYTES = SCR_WORDS * 4;
     static_assert(EW == 8 || EW == 16, "epilogue warps: 8 or 16");
-    static_assert(LN || WCOLS == LN_PART, "the LayerNorm partial sums are per (fp32-form) epilogue-warp column slice");
+    static_assert(LN || WCOLS == LN_PART || EPI == EPI_F32_GN128, "the LayerNorm partial sums are per (fp32-form) epilogue-warp column slice");
 };
 constexpr uint32_t TMEM_COLS = 512;
 
 template <int NCTA, int EPI>
 struct Cfg {
-    static constexpr int B_BYTES = (BN / NCTA) * BK * 2;
+    static constexpr int B_BYTES = (Geo<EPI>::BN / NCTA) * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int STAGES = NCTA == 2 ? (Geo<EPI>::TMA ? 3 : (Geo<EPI>::EW > 8 ? 4 : 5)) : (Geo<EPI>::TMA ? 2 : 3);
     static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + Geo<EPI>::EW * Geo<EPI>::SCR_BYTES + 512;
@@ -250,7 +252,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
                const __grid_constant__ CUtensorMap tmO2b, const TcParams p) {
     using C = Cfg<NCTA, EPI>;
     using G = Geo<EPI>;
-    constexpr int EPI_WARPS = G::EW, WCOLS = G::WCOLS, NBLK = G::NBLK, SCR_BYTES = G::SCR_BYTES;
+    constexpr int EPI_WARPS = G::EW, WCOLS = G::WCOLS, NBLK = G::NBLK, SCR_BYTES = G::SCR_BYTES, BN = G::BN;
     constexpr int STAGES = C::STAGES;
     constexpr int STAGE_BYTES = C::STAGE_BYTES;
     extern __shared__ uint8_t smem_raw[];
@@ -426,9 +428,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         uint32_t* scr = reinterpret_cast<uint32_t*>(scr_base + ew * SCR_BYTES);
         float* sbias = reinterpret_cast<float*>(scr + (G::TMA ? TMA_WARP_BYTES / 4 : (G::PTMA ? 1024 : 32 * SCR_STRIDE)));  // [WCOLS]
         constexpr bool packed = EPI != EPI_F32 && EPI != EPI_F32_EMIT && EPI != EPI_F32_TMA && EPI != EPI_F32_EMIT_RB && EPI != EPI_F32_UP &&
-                                EPI != EPI_F32_GN;
+                                EPI != EPI_F32_GN && EPI != EPI_F32_GN128;
         constexpr bool UP = EPI == EPI_F32_UP;  // plain fp32 form whose rows scatter into a 2x upsampled NHWC tensor
-        constexpr bool GN = EPI == EPI_F32_GN || EPI == EPI_F32_UP;  // forms that can emit GroupNorm partial sums (p.gn_part)
+        constexpr bool GN = EPI == EPI_F32_GN || EPI == EPI_F32_GN128 || EPI == EPI_F32_UP;  // forms that can emit GroupNorm partial sums (p.gn_part)
         constexpr bool EMIT = EPI == EPI_F32_EMIT || EPI == EPI_F32_EMIT_RB;
         constexpr bool RB = EPI == EPI_F32 || EPI == EPI_F32_EMIT_RB;  // forms that honour p.rowbias
         constexpr bool LN = G::LN;
@@ -910,6 +912,7 @@ void launch(const GemmProblem& g, cudaStream_t s) {
     p.N = g.N;
     p.Lr = g.Lr;
     p.tpb = ceil_div(g.Lr, BM);
+    constexpr int BN = Geo<EPI>::BN;
     p.ntn = ceil_div(g.N, BN);
     p.n_mtiles = g.nb * p.tpb;
     p.total_tiles = ceil_div(p.n_mtiles, NCTA) * p.ntn;
@@ -1115,7 +1118,10 @@ void gemm_tc_bf16(const GemmProblem& g, cudaStream_t s) {
         return;
     }
     if (g.gn_part) {
-        if (one_cta) launch<1, EPI_F32_GN>(g, s); else launch<2, EPI_F32_GN>(g, s);
+        static const bool no_n128 = getenv("PDM_GEMM_NO_N128") != nullptr;
+        if (one_cta) launch<1, EPI_F32_GN>(g, s);
+        else if (g.N == 128 && !no_n128) launch<2, EPI_F32_GN128>(g, s);  // C_out = 128: a 256-wide tile would be half padding
+        else launch<2, EPI_F32_GN>(g, s);
         return;
     }
     const int epi = g.out32 ? (tma_ok ? EPI_F32_TMA : ((g.stats || g.out2b) ? (g.rowbias ? EPI_F32_EMIT_RB : EPI_F32_EMIT) : EPI_F32))
