@@ -1,6 +1,15 @@
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "vae or sample_to_dir or linear" > gpurun_out/r2_t_vae.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2_t_vae.log
-tail -15 gpurun_out/r2_t_vae.log | cut -c1-250
-timeout 300 python tools/vae_bench.py --batch 32 --iters 3 > gpurun_out/r2_vae_bench5.log 2>&1; echo "rc=$?" >> gpurun_out/r2_vae_bench5.log
-grep -E "libpdm|rc=" gpurun_out/r2_vae_bench5.log | cut -c1-300
-PDM_GEMM_NO_N128=1 timeout 300 python tools/vae_bench.py --batch 32 --iters 3 2>&1 | grep '(libpdm)' | cut -c1-200
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r02_vae_launches.csv python - > gpurun_out/r2_vae_ncu.log 2>&1 <<'PY'
+import torch, sys
+sys.path.insert(0, '.')
+from panopticdiffusionmodels_b200.libs.autoencoder import get_model
+dev = torch.device("cuda:0")
+torch.manual_seed(0)
+vae = get_model(None, 0.23010).to(dev)
+z = torch.randn(32, 4, 32, 32, device=dev)
+vae.decode(z, max_batch=32)
+torch.cuda.synchronize()
+vae.decode(z, max_batch=32)
+torch.cuda.synchronize()
+PY
+ls -la gpurun_out/r02_vae_launches.csv
