@@ -1,15 +1,4 @@
 mkdir -p gpurun_out
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r02_vae_launches.csv python - > gpurun_out/r2_vae_ncu.log 2>&1 <<'PY'
-import torch, sys
-sys.path.insert(0, '.')
-from panopticdiffusionmodels_b200.libs.autoencoder import get_model
-dev = torch.device("cuda:0")
-torch.manual_seed(0)
-vae = get_model(None, 0.23010).to(dev)
-z = torch.randn(32, 4, 32, 32, device=dev)
-vae.decode(z, max_batch=32)
-torch.cuda.synchronize()
-vae.decode(z, max_batch=32)
-torch.cuda.synchronize()
-PY
-ls -la gpurun_out/r02_vae_launches.csv
+timeout 600 python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-eager-baseline --no-extra-configs --no-kernel-profile > gpurun_out/r02d_plain.json 2> gpurun_out/r02d_plain.err; echo "plain rc=$?"
+timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none -s 30000 --csv --log-file gpurun_out/r02d_launches.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-eager-baseline --no-extra-configs --no-kernel-profile > gpurun_out/r02d_ncu.log 2>&1; echo "ncu rc=$?"
+wc -l gpurun_out/r02d_launches.csv; ls -la gpurun_out/r02d_launches.csv
