@@ -71,6 +71,7 @@ struct Workspace {
     void* qkv = nullptr;      //                   [R, 3D]  act
     void* ao = nullptr;       // attention out     [R, D]   act
     void* u = nullptr;        // MLP hidden        [R, 4D]  act
+    void* u2 = nullptr;       // two-stream bf16 mode: the image block's MLP hidden [R1, 4D], kept across the mask block
     void* xb = nullptr;       // act copy of x     [R1, D]
     void* mxb = nullptr;      // act copy of mx    [R2, D]
     float* stats_x = nullptr;   // [R1, ceil(D/128), 2] per-row partial (sum, sum sq) of x  (deferred LayerNorm, bf16 mode)
@@ -122,6 +123,18 @@ __global__ void dup_weight_kernel(const float* __restrict__ w, bf16* __restrict_
 }
 }  // namespace
 // patch-embed weight [D, kk] fp32 -> bf16 [D, 2 kk] = [W | W] (operand of the [hi | lo] patch rows)
+// out [N, K1 + K2] = [a [N, K1] | b [N, K2]] (bf16): one GEMM over the concatenated K computes a.x1 + b.x2
+__global__ void concat_k_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, bf16* __restrict__ out, int N, int K1, int K2) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int K = K1 + K2;
+    if (i >= (long long)N * K) return;
+    const int n = (int)(i / K), k = (int)(i - (long long)n * K);
+    out[i] = k < K1 ? a[(long long)n * K1 + k] : b[(long long)n * K2 + (k - K1)];
+}
+__global__ void add_vec_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = a[i] + b[i];
+}
 void dup_weight_bf16(const float* w, bf16* out, int D, int kk, cudaStream_t s) {
     dup_weight_kernel<<<ceil_div(D * kk, 256), 256, 0, s>>>(w, out, D, kk);
     check_launch("dup_weight");
@@ -139,6 +152,11 @@ struct pdm_engine {
     std::vector<BlockW> in_b, out_b, in_bm, out_bm;
     BlockW mid_b, mid_bm;
     std::vector<LinearW> zc;  // zc[li] = zero_convs[2*li+1]
+    // two-stream bf16 mode: layer li's image-block fc2 and zero-conv as ONE GEMM over K = 4D + D,
+    //   x += [u_img | mx_act[:, :L1]] . [W_fc2 | W_zc]^T + (b_fc2 + b_zc)          (fz[li].w16 [D, 5D], fz[li].b [D])
+    std::vector<LinearW> fz;
+    std::vector<void*> fz_owned;
+    bool fuse_fc2_zc = getenv("PDM_NO_FC2_ZC_FUSION") == nullptr;
     std::map<std::string, FoldW> folds;  // keyed by "<block prefix>qkv" / "<block prefix>fc1"; allocated once (graphs bake pointers)
     LinearW ctx_lin;
     float* freqs = nullptr;
@@ -165,6 +183,7 @@ struct pdm_engine {
         if (wT_msk) cudaFree(wT_msk);
         if (wemb_img) cudaFree(wemb_img);
         if (wemb_msk) cudaFree(wemb_msk);
+        for (void* q : fz_owned) cudaFree(q);
         for (auto& kv : folds) {
             if (kv.second.w) cudaFree(kv.second.w);
             if (kv.second.d) cudaFree(kv.second.d);
@@ -353,6 +372,30 @@ struct pdm_engine {
                 fold_block("out_blocks_mask." + std::to_string(i) + ".", out_bm[i], s);
             }
         }
+        for (void* q : fz_owned) cudaFree(q);
+        fz_owned.clear();
+        fz.clear();
+        if (two) {
+            const int half = depth / 2;
+            for (int li = 0; li <= depth; ++li) {
+                const BlockW& b = li < half ? in_b[li] : (li == half ? mid_b : out_b[li - half - 1]);
+                const int K1 = b.fc2.K;
+                bf16* w = nullptr;
+                float* bias = nullptr;
+                PDM_CHECK_CUDA(cudaMalloc(&w, (size_t)D * (K1 + D) * sizeof(bf16)));
+                PDM_CHECK_CUDA(cudaMalloc(&bias, (size_t)D * sizeof(float)));
+                fz_owned.push_back(w);
+                fz_owned.push_back(bias);
+                const long long n = (long long)D * (K1 + D);
+                concat_k_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(b.fc2.w16, zc[li].w16, w, D, K1, D);
+                check_launch("concat_k");
+                add_vec_kernel<<<ceil_div(D, 256), 256, 0, s>>>(b.fc2.b, zc[li].b, bias, D);
+                check_launch("add_vec");
+                LinearW l;
+                l.w16 = w; l.b = bias; l.N = D; l.K = K1 + D;
+                fz.push_back(l);
+            }
+        }
         {
             const int kk = C * p * p;
             if (!wT_img) PDM_CHECK_CUDA(cudaMalloc(&wT_img, (size_t)kk * D * sizeof(float)));
@@ -398,6 +441,7 @@ struct pdm_engine {
         w.qkv = a.take(R * 3 * d * act);
         w.ao = a.take(R * d * act);
         w.u = a.take(R * cfg.mlp_ratio * d * act);
+        w.u2 = (two_m && w.prec == PDM_PREC_BF16) ? a.take(R1 * cfg.mlp_ratio * d * act) : nullptr;
         w.xb = a.take(R1 * d * act);
         w.mxb = two_m ? a.take(R2 * d * act) : nullptr;
         const size_t npart = (d + LN_PART - 1) / LN_PART;
@@ -565,9 +609,10 @@ struct pdm_engine {
     //   out2     where fc2 leaves the bf16 copy of the block output (nullptr: nobody reads it)
     //   out2b    optional second copy for rows >= out2b_row0 (tail of the concatenated mask stream)
     //   out_stats  fc2 also refreshes `stats` (the next consumer is an LN-folded GEMM, not a skip GEMM)
+    //   u_keep   non-null: stop after fc1 and leave the MLP hidden there (the caller fuses fc2 into a later GEMM)
     void run_block_dln(const BlockW& w, Workspace& ws, float* x, float* stats, const void* cur, int nb, int Lx,
                        const void* skipA1, const void* skipA2, void* out2, void* out2b, int out2b_row0, bool out_stats,
-                       cudaStream_t s) {
+                       cudaStream_t s, void* u_keep = nullptr) {
         const int R = nb * Lx;
         if (w.has_skip) {
             Scope sc(this, "gemm_skip", s);
@@ -600,9 +645,10 @@ struct pdm_engine {
             Scope sc(this, "gemm_fc1", s);
             GemmProblem g;
             g.A1 = ws.h; g.K1 = D; g.W16 = w.fc1_f.w; g.bias = w.fc1_f.d; g.ln_stats = stats; g.ln_D = D;
-            g.N = w.fc1.N; g.nb = 1; g.Lr = R; g.out2 = ws.u; g.gelu = true;
+            g.N = w.fc1.N; g.nb = 1; g.Lr = R; g.out2 = u_keep ? u_keep : ws.u; g.gelu = true;
             gemm_tc_bf16(g, s);
         }
+        if (u_keep) return;
         {
             Scope sc(this, "gemm_fc2", s);
             GemmProblem g;
@@ -619,12 +665,19 @@ struct pdm_engine {
     //   to_mask    the NEXT layer's mask block starts from cat(x, m): also store the new x rows into mx[:, :L1] (fp32,
     //              only if fp32_concat: the next mask block updates mx in place), into ws.mxb[:, :L1] (bf16) and their
     //              row sums into stats_mx -- the concat of libs/uvit_t2i.py:427 never runs as a kernel
+    //   fused      layer's [W_fc2 | W_zc] (fz[li]): the image block stopped after fc1 (hidden in ws.u2) and this GEMM finishes it too
     void run_zero_conv_dln(const LinearW& z, Workspace& ws, const void* A, void* out2, int nb, bool to_mask,
-                           bool fp32_concat, bool out_stats, cudaStream_t s) {
-        Scope sc(this, "gemm_zeroconv", s);
+                           bool fp32_concat, bool out_stats, cudaStream_t s, const LinearW* fused = nullptr) {
+        Scope sc(this, fused ? "gemm_fc2_zeroconv" : "gemm_zeroconv", s);
         GemmProblem g;
-        g.A1 = A; g.K1 = D; g.a1_bs = L2;
-        g.W16 = z.w16; g.bias = z.b; g.N = D;
+        if (fused) {
+            g.A1 = ws.u2; g.K1 = fused->K - D; g.a1_bs = L1;
+            g.A2 = A; g.K2 = D; g.a2_bs = L2;
+            g.W16 = fused->w16; g.bias = fused->b; g.N = D;
+        } else {
+            g.A1 = A; g.K1 = D; g.a1_bs = L2;
+            g.W16 = z.w16; g.bias = z.b; g.N = D;
+        }
         g.nb = nb; g.Lr = L1;
         g.resid = ws.x; g.resid_bs = L1; g.out32 = ws.x; g.out32_bs = L1; g.out2 = out2; g.out2_bs = L1;
         if (out_stats) {
@@ -659,28 +712,34 @@ struct pdm_engine {
                               j + 1 == half, s);
             return;
         }
+        // The image block of a layer and its mask block both start from the PREVIOUS layer's x (libs/uvit_t2i.py:419-436:
+        // mx = cat(x, m) is taken before x = blk(x)), and the layer ends with x = blk(x) + zero_conv(mx[:, :L1]).  So the image
+        // block stops after fc1 (hidden kept in ws.u2) and ONE GEMM over K = 4D + D finishes both sums: x is read and written
+        // once per layer instead of twice, and the image-stream fc2 launch disappears.
+        const bool fuse = fuse_fc2_zc && ws.u2 != nullptr && (int)fz.size() == depth + 1;
+        void* keep = fuse ? ws.u2 : nullptr;
         const void* cur_x = ws.xb;
         int li = 0;
         for (int i = 0; i < half; ++i, ++li) {
-            run_block_dln(in_b[i], ws, ws.x, ws.stats_x, cur_x, nb, L1, nullptr, nullptr, nullptr, nullptr, 0, false, s);
+            run_block_dln(in_b[i], ws, ws.x, ws.stats_x, cur_x, nb, L1, nullptr, nullptr, nullptr, nullptr, 0, false, s, keep);
             run_block_dln(in_bm[i], ws, ws.mx, ws.stats_mx, ws.mxb, nb, L2, nullptr, nullptr, ws.skipm[i], ws.mxb, L1, true, s);
-            run_zero_conv_dln(zc[li], ws, ws.skipm[i], ws.skipx[i], nb, true, true, true, s);
+            run_zero_conv_dln(zc[li], ws, ws.skipm[i], ws.skipx[i], nb, true, true, true, s, fuse ? &fz[li] : nullptr);
             cur_x = ws.skipx[i];
         }
         // mid layer: its outputs feed skip GEMMs (no LayerNorm on them) -> bf16 copies only
-        run_block_dln(mid_b, ws, ws.x, ws.stats_x, cur_x, nb, L1, nullptr, nullptr, nullptr, nullptr, 0, false, s);
+        run_block_dln(mid_b, ws, ws.x, ws.stats_x, cur_x, nb, L1, nullptr, nullptr, nullptr, nullptr, 0, false, s, keep);
         run_block_dln(mid_bm, ws, ws.mx, ws.stats_mx, ws.mxb, nb, L2, nullptr, nullptr, ws.h, ws.mxb, L1, false, s);
-        run_zero_conv_dln(zc[li], ws, ws.h, ws.xb, nb, true, false, false, s);
+        run_zero_conv_dln(zc[li], ws, ws.h, ws.xb, nb, true, false, false, s, fuse ? &fz[li] : nullptr);
         ++li;
         for (int j = 0; j < half; ++j, ++li) {
             const bool more = j + 1 < half;
             run_block_dln(out_b[j], ws, ws.x, ws.stats_x, nullptr, nb, L1, ws.xb, ws.skipx[half - 1 - j], nullptr, nullptr, 0,
-                          false, s);
+                          false, s, keep);
             run_block_dln(out_bm[j], ws, ws.mx, ws.stats_mx, nullptr, nb, L2, ws.mxb, ws.skipm[half - 1 - j], ws.h,
                           more ? ws.mxb : nullptr, L1, false, s);
             // (last layer: bf16 copy + row sums of the final image stream for the decoder GEMM; the final mask stream's bf16
             //  copy is ws.h, left by the mask block's fc2)
-            run_zero_conv_dln(zc[li], ws, ws.h, ws.xb, nb, more, false, !more, s);
+            run_zero_conv_dln(zc[li], ws, ws.h, ws.xb, nb, more, false, !more, s, fuse ? &fz[li] : nullptr);
         }
     }
 
