@@ -1,13 +1,7 @@
-mkdir -p gpurun_out
-timeout 1200 python bench.py > gpurun_out/r2_bench_h.json 2> gpurun_out/r2_bench_h.err; echo "bench rc=$?"
-python - <<'PY'
-import json
-d=json.loads(open('gpurun_out/r2_bench_h.json').read().strip().splitlines()[-1])
-print('value',d['value'],'e2e',d['e2e']['value'],'launches',d['gpu_launches'],'clocks',d['clocks'])
-print('roofline',d['roofline']['frac'],d['roofline']['achieved'],'attn',d['roofline_attention']['achieved'], d['roofline_attention']['share_of_step'])
-print('ms_per_nnet_step',d['ms_per_nnet_step'],'frac',d['frac_of_bf16_peak'],'tf',d['model_tflops_per_gpu'])
-print('vae',d.get('vae_decode'))
-for k,v in d.get('configs',{}).items(): print(k, v.get('samples_per_s'), v.get('ms_per_nnet_step'), v.get('model_tflops_per_gpu'), v.get('frac_of_bf16_peak'), v.get('roofline',{}).get('achieved'), v.get('roofline',{}).get('frac'), v.get('roofline_attention',{}).get('achieved'), v.get('roofline_attention',{}).get('share_of_step'))
-PY
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 38000 -c 7900 --csv --log-file gpurun_out/r02e_launches.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-eager-baseline --no-extra-configs --no-kernel-profile > gpurun_out/r02e_ncu.log 2>&1; echo "ncu rc=$?"
-wc -l gpurun_out/r02e_launches.csv
+mkdir -p gpurun_out /tmp/prof
+S="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-eager-baseline --no-extra-configs --no-kernel-profile --nfe 10"
+timeout 300 $S > /tmp/prof/plain.json 2>/tmp/prof/plain.err; echo "plain rc=$?"
+timeout 900 ncu --set full --clock-control none -k regex:'im2col_patch|embed_extras_emit|conv3x3_tok|update_kernel|gemm_tc_kernelILi2ELi7E|gemm_tc_kernel<2, 7>' -s 14 -c 7 -o /tmp/prof/r02_prof_hbm2 $S > /tmp/prof/ncu.log 2>&1; echo "ncu rc=$?"
+ls -la /tmp/prof/
+python tools/summarise_ncu.py /tmp/prof/r02_prof_hbm2.ncu-rep gpurun_out/r02_hbm_kernels_v2_ncu.md "r02 -- embed / head / update kernels of the end-of-round bf16 path (ncu --set full inside bench.py, config 2)" "ncu --set full --clock-control none -k regex:'im2col_patch|embed_extras_emit|conv3x3_tok|update_kernel|gemm_tc_kernel<2, 7>' -s 14 -c 7 $S" 2>&1 | tail -3
+cat gpurun_out/r02_hbm_kernels_v2_ncu.md | cut -c1-400
