@@ -130,12 +130,14 @@ class FrozenAutoencoderKL(nn.Module):
 
     # ---- engine management (same scheme as libs.uvit_t2i.UViT) ----
     def _release(self):
-        if self.__dict__.get("_handle") is not None:
+        h = self.__dict__.get("_handle")
+        if h is not None:
+            # plain dict write: nn.Module.__setattr__ is not usable any more when this runs from __del__ at interpreter exit
+            self.__dict__["_handle"] = None
             try:
-                _lib.lib().pdm_vae_destroy(self._handle)
+                _lib.lib().pdm_vae_destroy(h)
             except Exception:
                 pass
-            self._handle = None
 
     def __del__(self):
         self._release()

@@ -165,12 +165,14 @@ class UViT(nn.Module):
                               self.num_panoptic_class, int(self.enable_panoptic), int(self.separate))
 
     def _release(self):
-        if self.__dict__.get("_handle") is not None:
+        h = self.__dict__.get("_handle")
+        if h is not None:
+            # plain dict write: nn.Module.__setattr__ is not usable any more when this runs from __del__ at interpreter exit
+            self.__dict__["_handle"] = None
             try:
-                _lib.lib().pdm_destroy(self._handle)
+                _lib.lib().pdm_destroy(h)
             except Exception:
                 pass
-            self._handle = None
 
     def __del__(self):
         self._release()
