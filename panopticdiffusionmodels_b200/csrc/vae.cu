@@ -10,9 +10,12 @@
 // tap (ky, kx) is one TMA box of the activation shifted by (ky - 1, kx - 1) whose out-of-bounds part is zero-filled by the
 // TMA unit (= the padding); nothing is ever unfolded in memory.  Bias, the residual add (x += conv2(...)) and the fp32 store
 // are the GEMM epilogue.  1x1 convolutions (nin_shortcut, q / k / v / proj_out) are plain GEMMs on the flat [pixels, C] view.
-// GroupNorm (32 groups, eps 1e-6) is a statistics pass (fp32 partial sums in a fixed order, fp64 combine) + one fused
-// normalise * gamma + beta -> swish -> bf16 pass that writes the next convolution's operand; the nearest-neighbour upsample
-// is fused into the operand write of the Upsample convolution.  The single-head 512-channel attention of the mid block
+// GroupNorm (32 groups, eps 1e-6): the fp32 partial sums per (image, 32-row slab, group) are emitted by the epilogue of the
+// GEMM that produces the tensor (GemmProblem::gn_part; a stand-alone statistics pass remains for the outputs of conv_in and
+// of the attention), combined in fp64 in a fixed order, and one fused normalise * gamma + beta -> swish -> bf16 pass writes
+// the next convolution's operand.  "Nearest 2x upsample -> 3x3 convolution" runs as four 2x2 phase convolutions over the
+// LOW-resolution operand (repack_up_phases_kernel; GemmProblem::conv_up): 16 instead of 36 MACs per output element and the
+// upsampled tensor is never materialised as an operand.  conv_out (3 output channels) uses warp-level mma.sync.  The single-head 512-channel attention of the mid block
 // (1024 tokens at 256 px) is per image S = q k^T (GEMM) -> row softmax -> O = P V (GEMM against V^T, which a GEMM with the
 // roles of weight and activation swapped produces directly; v's bias commutes with the softmax and is folded into
 // proj_out's).
