@@ -17,7 +17,10 @@
 //                                residual tile in by TMA, row-domain add on swizzled staging tiles, tiles out by TMA stores
 //               PACK / LN / LN_GELU[_W16]   bf16-only output, packed before the transpose; LN*: LayerNorm folded into the
 //                                weight, 1/std per accumulator row applied here; _W16: 16 epilogue warps (fc1, K <= 512)
-// Rings: STAGES-deep smem ring, 2-deep TMEM accumulator ring (2 x 256 columns).
+//               F32_UP / F32_GN / F32_GN128   VAE decoder forms of the fp32 epilogue (see the enum below)
+// A operand modes: plain rows (3-D map), [A1 | A2] concatenated along K (long skip; fc2 + zero-conv of a two-stream layer),
+// implicit 3x3 convolution over NHWC (4-D map, one shifted box per tap), and the 2x2 phase convolutions of an upsample.
+// Rings: STAGES-deep smem ring, 2-deep TMEM accumulator ring (2 x BN columns; BN = 256, 128 for _GN128).
 // The long-skip concat is never materialised (K loop streams A1 then A2); row views use the map's batch coordinate.
 #include <cstdlib>
 #include <map>
@@ -46,8 +49,10 @@ constexpr int BK = 64;  // the N tile is per form: Geo<EPI>::BN (256; 128 for EP
 constexpr int A_BYTES = BM * BK * 2;
 constexpr int SCR_STRIDE = 36;  // 32-bit words per scratch row: 128 B payload + 16 B pad (16 B aligned, conflict-free)
 enum { EPI_F32 = 0, EPI_PACK = 1, EPI_LN = 2, EPI_LN_GELU = 3, EPI_F32_EMIT = 4, EPI_LN_GELU_W16 = 5, EPI_F32_TMA = 6,
-       EPI_F32_EMIT_RB = 7, EPI_F32_UP = 8, EPI_F32_GN = 9,
-       EPI_F32_GN128 = 10 };  // _GN128: the _GN form on a 256 x 128 pair tile (C_out = 128 convolutions: no half-empty MMAs)  // _RB: EMIT + per-row bias table (the patch-embed GEMM: positional rows, bf16 copies, row sums)
+       EPI_F32_EMIT_RB = 7,  // EMIT + per-row bias table (the patch-embed GEMM: positional rows, bf16 copies, row sums)
+       EPI_F32_UP = 8,       // plain fp32 form whose rows scatter into a 2x upsampled NHWC tensor (VAE upsample phase convolutions)
+       EPI_F32_GN = 9,       // plain / += fp32 form that also emits GroupNorm partial sums of its output (VAE 3x3 convolutions)
+       EPI_F32_GN128 = 10 }; // the _GN form on a 256 x 128 pair tile (C_out = 128 convolutions: no half-empty MMAs)
 constexpr int TMA_WARP_BYTES = 3 * 4096 + 2048;  // EPI_F32_TMA: 3 fp32 [32 x 32] staging tiles + 1 bf16 [32 x 32] tile per warp
 
 // Epilogue geometry per form.  Each epilogue warp covers one TMEM lane quarter x WCOLS accumulator columns.  The
