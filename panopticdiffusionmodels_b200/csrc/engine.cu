@@ -372,20 +372,26 @@ struct pdm_engine {
                 fold_block("out_blocks_mask." + std::to_string(i) + ".", out_bm[i], s);
             }
         }
-        for (void* q : fz_owned) cudaFree(q);
-        fz_owned.clear();
         fz.clear();
         if (two) {
             const int half = depth / 2;
+            // allocated once and rewritten in place on every finalize (like the folded weights): captured CUDA graphs and
+            // cached tensor maps keep pointing at valid, current data when parameters are updated
+            const bool fresh = fz_owned.empty();
             for (int li = 0; li <= depth; ++li) {
                 const BlockW& b = li < half ? in_b[li] : (li == half ? mid_b : out_b[li - half - 1]);
                 const int K1 = b.fc2.K;
                 bf16* w = nullptr;
                 float* bias = nullptr;
-                PDM_CHECK_CUDA(cudaMalloc(&w, (size_t)D * (K1 + D) * sizeof(bf16)));
-                PDM_CHECK_CUDA(cudaMalloc(&bias, (size_t)D * sizeof(float)));
-                fz_owned.push_back(w);
-                fz_owned.push_back(bias);
+                if (fresh) {
+                    PDM_CHECK_CUDA(cudaMalloc(&w, (size_t)D * (K1 + D) * sizeof(bf16)));
+                    PDM_CHECK_CUDA(cudaMalloc(&bias, (size_t)D * sizeof(float)));
+                    fz_owned.push_back(w);
+                    fz_owned.push_back(bias);
+                } else {
+                    w = (bf16*)fz_owned[2 * li];
+                    bias = (float*)fz_owned[2 * li + 1];
+                }
                 const long long n = (long long)D * (K1 + D);
                 concat_k_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(b.fc2.w16, zc[li].w16, w, D, K1, D);
                 check_launch("concat_k");

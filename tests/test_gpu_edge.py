@@ -268,3 +268,33 @@ def test_c_abi_rejects_malformed_plans():
     assert run(plan, plan.shape[0]) == 0                       # and the handle still works
     torch.cuda.synchronize()
     assert torch.equal(ref, oz)
+
+
+@pytest.mark.parametrize("separate", [False, True])
+def test_parameter_update_after_first_use(separate):
+    """Weights changed in place after an engine (and a captured CUDA graph) exists: the next call re-uploads them, rebuilds the
+    derived buffers IN PLACE (bf16 copies, LayerNorm-folded weights, the concatenated fc2 | zero-conv weight of a two-stream
+    layer) and the replayed graph computes with the new values -- bit-equal to a fresh module built from the same state."""
+    from panopticdiffusionmodels_b200.libs.uvit_t2i import UViT
+    from panopticdiffusionmodels_b200.sampling import JointSampler
+    net, _ = make_net(separate, "bf16")
+    g = torch.Generator().manual_seed(11)
+    B = 2
+    ctx = torch.randn(B, 5, 32, generator=g).to(DEV)
+    ec = torch.randn(5, 32, generator=g).to(DEV)
+    z0 = torch.randn(B, 4, 8, 8, generator=g).to(DEV)
+    m0 = torch.randn(B, 8, 8, 8, generator=g).to(DEV)
+    sampler = JointSampler(net, z_shape=(4, 8, 8), scale=2.0, sample_steps=8)
+    z_old, p_old = (v.clone() for v in sampler.sample(ctx, ec, z0, m0))
+    with torch.no_grad():
+        for k, p in net.named_parameters():
+            if k.endswith("mlp.fc2.weight") or k.endswith("norm2.weight") or k.startswith("zero_convs") or k == "pos_embed":
+                p.mul_(1.25)
+    z_new, p_new = (v.clone() for v in sampler.sample(ctx, ec, z0, m0))
+    assert not torch.equal(z_old, z_new)
+    fresh = UViT(separate=separate, **TINY)
+    fresh.load_state_dict({k: v.detach().cpu() for k, v in net.state_dict().items()}, strict=True)
+    fresh = fresh.to(DEV).eval()
+    fresh.precision = "bf16"
+    z_ref, p_ref = JointSampler(fresh, z_shape=(4, 8, 8), scale=2.0, sample_steps=8).sample(ctx, ec, z0, m0)
+    assert torch.equal(z_new, z_ref) and torch.equal(p_new, p_ref)
