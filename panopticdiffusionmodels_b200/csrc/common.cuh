@@ -107,6 +107,10 @@ struct GemmProblem {
     // per-row partial sums (sum, sum of squares) over each 128-column slice: stats[row][ceil(N/128)][2]
     void* out2b = nullptr;
     int out2b_bs = 0, out2b_row0 = 0, out2b_mod = 0;  // rows with (row % out2b_mod if out2b_mod else row) >= out2b_row0
+    // fp32 store filter: out32 is written only for rows with (row % out32_mod if out32_mod else row) >= out32_row0 (0 = all
+    // rows).  For a residual GEMM whose fp32 result nobody reads (the next block starts with a long-skip GEMM fed by the bf16
+    // copies, or the head follows): the value is still formed (residual read, bf16 copies, row sums), only the dead store goes.
+    int out32_row0 = 0, out32_mod = 0;
     float* stats = nullptr;
     int stats_bs = 0;
     float* statsb = nullptr;  // same values, second destination (rows of the concatenated mask stream)

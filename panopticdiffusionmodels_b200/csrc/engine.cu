@@ -157,6 +157,11 @@ struct pdm_engine {
     std::vector<LinearW> fz;
     std::vector<void*> fz_owned;
     bool fuse_fc2_zc = getenv("PDM_NO_FC2_ZC_FUSION") == nullptr;
+    // bf16 mode: a block whose successor starts with a long-skip GEMM (fed by bf16 copies, writes a fresh fp32 stream), or
+    // that is followed by the head, produces an fp32 residual nobody reads; its fc2 skips that store (mid + all out blocks;
+    // two-stream: also the image rows of an in-block mask stream, which the layer's zero-conv GEMM overwrites)
+    bool dead_store_elim = getenv("PDM_KEEP_DEAD_STORES") == nullptr;
+    static constexpr int NO_F32_ROWS = 0x7fffffff;
     std::map<std::string, FoldW> folds;  // keyed by "<block prefix>qkv" / "<block prefix>fc1"; allocated once (graphs bake pointers)
     LinearW ctx_lin;
     float* freqs = nullptr;
@@ -618,7 +623,7 @@ struct pdm_engine {
     //   u_keep   non-null: stop after fc1 and leave the MLP hidden there (the caller fuses fc2 into a later GEMM)
     void run_block_dln(const BlockW& w, Workspace& ws, float* x, float* stats, const void* cur, int nb, int Lx,
                        const void* skipA1, const void* skipA2, void* out2, void* out2b, int out2b_row0, bool out_stats,
-                       cudaStream_t s, void* u_keep = nullptr) {
+                       cudaStream_t s, void* u_keep = nullptr, int x32_row0 = 0) {
         const int R = nb * Lx;
         if (w.has_skip) {
             Scope sc(this, "gemm_skip", s);
@@ -662,6 +667,8 @@ struct pdm_engine {
             g.nb = 1; g.Lr = R; g.resid = x; g.out32 = x; g.out2 = out2;
             g.out2b = out2b; g.out2b_row0 = out2b_row0; g.out2b_mod = Lx;  // flat rows: the filter is per sample
             g.stats = out_stats ? stats : nullptr;
+            // fp32 rows of the block output that nobody reads are not stored (see GemmProblem::out32_row0)
+            if (dead_store_elim && (out2 || out2b || g.stats)) { g.out32_row0 = x32_row0; g.out32_mod = x32_row0 ? Lx : 0; }
             gemm_tc_bf16(g, s);
         }
     }
@@ -673,7 +680,8 @@ struct pdm_engine {
     //              row sums into stats_mx -- the concat of libs/uvit_t2i.py:427 never runs as a kernel
     //   fused      layer's [W_fc2 | W_zc] (fz[li]): the image block stopped after fc1 (hidden in ws.u2) and this GEMM finishes it too
     void run_zero_conv_dln(const LinearW& z, Workspace& ws, const void* A, void* out2, int nb, bool to_mask,
-                           bool fp32_concat, bool out_stats, cudaStream_t s, const LinearW* fused = nullptr) {
+                           bool fp32_concat, bool out_stats, cudaStream_t s, const LinearW* fused = nullptr,
+                           bool x_dead = false) {
         Scope sc(this, fused ? "gemm_fc2_zeroconv" : "gemm_zeroconv", s);
         GemmProblem g;
         if (fused) {
@@ -698,6 +706,8 @@ struct pdm_engine {
                 g.statsb = ws.stats_mx; g.statsb_bs = L2;
             }
         }
+        // x of a layer whose NEXT image block starts with a long-skip GEMM (or the head) is only read through its bf16 copy
+        if (fused && x_dead && dead_store_elim && (out2 || to_mask)) g.out32_row0 = NO_F32_ROWS;
         gemm_tc_bf16(g, s);
     }
 
@@ -711,11 +721,12 @@ struct pdm_engine {
                 run_block_dln(in_b[i], ws, ws.x, ws.stats_x, cur, nb, Lx, nullptr, nullptr, ws.skipx[i], nullptr, 0, true, s);
                 cur = ws.skipx[i];
             }
-            run_block_dln(mid_b, ws, ws.x, ws.stats_x, cur, nb, Lx, nullptr, nullptr, ws.xb, nullptr, 0, false, s);
+            run_block_dln(mid_b, ws, ws.x, ws.stats_x, cur, nb, Lx, nullptr, nullptr, ws.xb, nullptr, 0, false, s, nullptr,
+                          NO_F32_ROWS);
             // (the last block leaves the bf16 copy and the row sums of the FINAL stream: operands of the decoder GEMMs)
             for (int j = 0; j < half; ++j)
                 run_block_dln(out_b[j], ws, ws.x, ws.stats_x, nullptr, nb, Lx, ws.xb, ws.skipx[half - 1 - j], ws.xb, nullptr, 0,
-                              j + 1 == half, s);
+                              j + 1 == half, s, nullptr, j + 1 == half ? 0 : NO_F32_ROWS);  // (the gt / generic head reads fp32 x)
             return;
         }
         // The image block of a layer and its mask block both start from the PREVIOUS layer's x (libs/uvit_t2i.py:419-436:
@@ -728,24 +739,28 @@ struct pdm_engine {
         int li = 0;
         for (int i = 0; i < half; ++i, ++li) {
             run_block_dln(in_b[i], ws, ws.x, ws.stats_x, cur_x, nb, L1, nullptr, nullptr, nullptr, nullptr, 0, false, s, keep);
-            run_block_dln(in_bm[i], ws, ws.mx, ws.stats_mx, ws.mxb, nb, L2, nullptr, nullptr, ws.skipm[i], ws.mxb, L1, true, s);
+            // (mask stream of an in-block layer: rows [0, L1) of mx are rewritten by the layer's zero-conv GEMM -> fp32 store of
+            //  the tail rows only)
+            run_block_dln(in_bm[i], ws, ws.mx, ws.stats_mx, ws.mxb, nb, L2, nullptr, nullptr, ws.skipm[i], ws.mxb, L1, true, s,
+                          nullptr, L1);
             run_zero_conv_dln(zc[li], ws, ws.skipm[i], ws.skipx[i], nb, true, true, true, s, fuse ? &fz[li] : nullptr);
             cur_x = ws.skipx[i];
         }
         // mid layer: its outputs feed skip GEMMs (no LayerNorm on them) -> bf16 copies only
         run_block_dln(mid_b, ws, ws.x, ws.stats_x, cur_x, nb, L1, nullptr, nullptr, nullptr, nullptr, 0, false, s, keep);
-        run_block_dln(mid_bm, ws, ws.mx, ws.stats_mx, ws.mxb, nb, L2, nullptr, nullptr, ws.h, ws.mxb, L1, false, s);
-        run_zero_conv_dln(zc[li], ws, ws.h, ws.xb, nb, true, false, false, s, fuse ? &fz[li] : nullptr);
+        run_block_dln(mid_bm, ws, ws.mx, ws.stats_mx, ws.mxb, nb, L2, nullptr, nullptr, ws.h, ws.mxb, L1, false, s, nullptr,
+                      NO_F32_ROWS);
+        run_zero_conv_dln(zc[li], ws, ws.h, ws.xb, nb, true, false, false, s, fuse ? &fz[li] : nullptr, true);
         ++li;
         for (int j = 0; j < half; ++j, ++li) {
             const bool more = j + 1 < half;
             run_block_dln(out_b[j], ws, ws.x, ws.stats_x, nullptr, nb, L1, ws.xb, ws.skipx[half - 1 - j], nullptr, nullptr, 0,
                           false, s, keep);
             run_block_dln(out_bm[j], ws, ws.mx, ws.stats_mx, nullptr, nb, L2, ws.mxb, ws.skipm[half - 1 - j], ws.h,
-                          more ? ws.mxb : nullptr, L1, false, s);
+                          more ? ws.mxb : nullptr, L1, false, s, nullptr, more ? NO_F32_ROWS : 0);
             // (last layer: bf16 copy + row sums of the final image stream for the decoder GEMM; the final mask stream's bf16
             //  copy is ws.h, left by the mask block's fc2)
-            run_zero_conv_dln(zc[li], ws, ws.h, ws.xb, nb, more, false, !more, s, fuse ? &fz[li] : nullptr);
+            run_zero_conv_dln(zc[li], ws, ws.h, ws.xb, nb, more, false, !more, s, fuse ? &fz[li] : nullptr, more);
         }
     }
 

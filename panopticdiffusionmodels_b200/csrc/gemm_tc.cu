@@ -107,6 +107,7 @@ struct TcParams {
     bf16* out2b;      // second bf16 copy, rows >= out2b_row0 of each batch only
     long long out2b_bs;
     int out2b_row0, out2b_mod;  // row filter: (row % out2b_mod if out2b_mod else row) >= out2b_row0
+    int out32_row0, out32_mod;  // the same filter for the fp32 store itself (0 = store every row)
     float* stats;     // [rows][npart][2] partial (sum, sum of squares) per LN_PART-column slice
     long long stats_bs;
     float* statsb;
@@ -714,6 +715,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
                         okb |= (t >= p.out2b_row0 ? 1u : 0u) << ps;
                     }
                 }
+                uint32_t ok32 = 0xffu;  // bit ps: row ps * 4 + rsub passes the fp32 store filter
+                if (p.out32_row0) {
+                    ok32 = 0;
+#pragma unroll
+                    for (int ps = 0; ps < 8; ++ps) {
+                        int t = trow0 + ps * 4 + rsub;
+                        if (p.out32_mod) t %= p.out32_mod;
+                        ok32 |= (t >= p.out32_row0 ? 1u : 0u) << ps;
+                    }
+                }
                 float s1[8], s2[8];  // deferred LayerNorm: this lane's share of the row sums over the warp's column slice
 #pragma unroll
                 for (int ps = 0; ps < 8; ++ps) s1[ps] = s2[ps] = 0.f;
@@ -810,7 +821,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
                                 *reinterpret_cast<float4*>(p.out32 + ((long long)(2 * gy + p.up_a) * (2 * p.conv_W) + 2 * gx + p.up_b) * p.N + col) = a;
                             }
                         } else if (col_ok && row_ok) {
-                            *reinterpret_cast<float4*>(po) = a;
+                            if ((ok32 >> ps) & 1u) *reinterpret_cast<float4*>(po) = a;
                             if (pob) *reinterpret_cast<float4*>(pob) = a;
                             if (ph) *reinterpret_cast<uint2*>(ph) = make_uint2(pack2(a.x, a.y), pack2(a.z, a.w));
                             if constexpr (EMIT) {
@@ -934,6 +945,8 @@ void launch(const GemmProblem& g, cudaStream_t s) {
     p.out2b_bs = g.out2b_bs ? g.out2b_bs : g.Lr;
     p.out2b_row0 = g.out2b_row0;
     p.out2b_mod = g.out2b_mod;
+    p.out32_row0 = g.out32_row0;
+    p.out32_mod = g.out32_mod;
     p.stats = g.stats;
     p.stats_bs = g.stats_bs ? g.stats_bs : g.Lr;
     p.statsb = g.statsb;
@@ -1117,7 +1130,7 @@ void gemm_tc_bf16(const GemmProblem& g, cudaStream_t s) {
     static const int tma_maxk = getenv("PDM_GEMM_TMA_MAXK") ? atoi(getenv("PDM_GEMM_TMA_MAXK")) : 1024;
     static const bool tma_noresid = getenv("PDM_GEMM_TMA_NORESID") != nullptr;
     const bool tma_ok = tma_epi && g.out32 && (g.resid || tma_noresid) && !g.gelu && g.N % 32 == 0 && K_total(g) <= tma_maxk &&
-                        (!g.out2b || (g.out2b_row0 == 0 && g.out2b_mod == 0));
+                        (!g.out2b || (g.out2b_row0 == 0 && g.out2b_mod == 0)) && g.out32_row0 == 0;
     if (g.conv_up) {
         if (one_cta) launch<1, EPI_F32_UP>(g, s); else launch<2, EPI_F32_UP>(g, s);
         return;
