@@ -1129,6 +1129,8 @@ void gemm_tc_bf16(const GemmProblem& g, cudaStream_t s) {
     static const bool tma_epi = getenv("PDM_GEMM_NO_TMA_EPI") == nullptr;
     static const int tma_maxk = getenv("PDM_GEMM_TMA_MAXK") ? atoi(getenv("PDM_GEMM_TMA_MAXK")) : 1024;
     static const bool tma_noresid = getenv("PDM_GEMM_TMA_NORESID") != nullptr;
+    // 16 epilogue warps for the fc1 form up to this K (above it the MMAs dominate and the 4-stage ring costs more than it gains)
+    static const int w16_maxk = getenv("PDM_GEMM_W16_MAXK") ? atoi(getenv("PDM_GEMM_W16_MAXK")) : 512;
     const bool tma_ok = tma_epi && g.out32 && (g.resid || tma_noresid) && !g.gelu && g.N % 32 == 0 && K_total(g) <= tma_maxk &&
                         (!g.out2b || (g.out2b_row0 == 0 && g.out2b_mod == 0)) && g.out32_row0 == 0;
     if (g.conv_up) {
@@ -1143,7 +1145,7 @@ void gemm_tc_bf16(const GemmProblem& g, cudaStream_t s) {
         return;
     }
     const int epi = g.out32 ? (tma_ok ? EPI_F32_TMA : ((g.stats || g.out2b) ? (g.rowbias ? EPI_F32_EMIT_RB : EPI_F32_EMIT) : EPI_F32))
-                            : (ln ? (g.gelu ? (g.K1 <= 512 ? EPI_LN_GELU_W16 : EPI_LN_GELU) : EPI_LN) : EPI_PACK);
+                            : (ln ? (g.gelu ? (g.K1 <= w16_maxk ? EPI_LN_GELU_W16 : EPI_LN_GELU) : EPI_LN) : EPI_PACK);
     if (one_cta) {
         if (epi == EPI_F32) launch<1, EPI_F32>(g, s);
         else if (epi == EPI_F32_TMA) launch<1, EPI_F32_TMA>(g, s);
